@@ -1,0 +1,43 @@
+"""Build the UNMODIFIED reference rasterizer (RAST = submodules/diff-gaussian-rasterizer-depth)
+for sm_100 and drop only the resulting extension module into oracle/_ref/.
+
+TEST INFRASTRUCTURE. Reference sources are compiled where they lie (a scratch copy under /tmp is
+needed because setuptools writes build/ next to setup.py and /root/reference is read-only); no
+reference source enters this repository. oracle/_ref/ is git-ignored but travels to the GPU box.
+
+The only deviation from `python setup.py build_ext` is `-include cstdint` (gcc 13 no longer pulls
+<cstdint> in transitively; rasterizer_impl.h:24 uses std::uintptr_t) and the explicit arch list.
+"""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+REF = "/root/reference/submodules/diff-gaussian-rasterizer-depth"
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+
+
+def main():
+    if not os.path.isdir(REF):
+        print("reference not present; keeping whatever is in oracle/_ref/")
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    if glob.glob(os.path.join(OUT, "_C_depth*.so")) and "--force" not in sys.argv:
+        print("oracle/_ref already built")
+        return 0
+    tmp = "/tmp/rtg_refbuild"
+    shutil.rmtree(tmp, ignore_errors=True)
+    shutil.copytree(REF, tmp)
+    env = dict(os.environ, NVCC_APPEND_FLAGS="-include cstdint", TORCH_CUDA_ARCH_LIST="10.0", MAX_JOBS="8")
+    subprocess.check_call([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=tmp, env=env)
+    so = glob.glob(os.path.join(tmp, "diff_gaussian_rasterization_depth", "_C_depth*.so"))
+    assert so, "reference build produced no extension"
+    shutil.copy(so[0], OUT)
+    print("built", os.path.join(OUT, os.path.basename(so[0])))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
