@@ -1,0 +1,153 @@
+/*
+ * rtg_splat_b200.h -- C ABI of librtg_splat_b200.so (sm_100a).
+ *
+ * Drop-in boundary for RTG-SLAM's data-parallel hot path. Every entry point names the
+ * reference interface it replaces ("RAST/" = submodules/diff-gaussian-rasterizer-depth/ of
+ * MisEty/RTG-SLAM). Plain pointers and sizes only; no torch types. All device pointers are
+ * CUDA device memory on the current device, fp32 / int32, contiguous. Every call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and
+ * performs no host<->device synchronisation.
+ *
+ * Return value: 0 on success, negative RtgStatus on error; rtg_last_error() holds the message
+ * (thread-local).
+ */
+#ifndef RTG_SPLAT_B200_H
+#define RTG_SPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum RtgStatus {
+    RTG_OK = 0,
+    RTG_ERR_INVALID_ARGUMENT = -1,
+    RTG_ERR_CUDA = -2,
+    RTG_ERR_UNSUPPORTED = -3,
+};
+
+const char *rtg_last_error(void);
+int rtg_version(void);
+
+/* Per-view constants: replaces GaussianRasterizationSettings
+ * (RAST/diff_gaussian_rasterization_depth/__init__.py:284-303) as marshalled by
+ * RasterizeGaussiansCUDA (RAST/rasterize_points.cu:37-64). Matrices stay on the device, exactly as
+ * the reference passes them (viewmatrix = W2C transposed, projmatrix = full projection,
+ * scene/cameras.py:96-110). */
+typedef struct RtgSplatView {
+    int32_t image_height, image_width;
+    float tanfovx, tanfovy;
+    float cx, cy;
+    float scale_modifier;
+    float color_sigma;
+    float opaque_threshold;
+    float depth_threshold;
+    float normal_threshold; /* cosine */
+    float T_threshold;
+    int32_t sh_degree;
+    int32_t prefiltered;
+    const float *viewmatrix; /* device, 16 floats */
+    const float *projmatrix; /* device, 16 floats */
+    const float *campos;     /* device, 3 floats  */
+    const float *bg;         /* device, 3 floats  */
+} RtgSplatView;
+
+/* Device counters written by rtg_splat_forward (int32 each). */
+enum { RTG_CNT_NUM_RENDERED = 0, RTG_CNT_NUM_TILES = 1, RTG_CNT_OVERFLOW = 2, RTG_CNT_MAX_TILE_LEN = 3, RTG_CNT_WORDS = 8 };
+
+/* Sizes of the three state buffers kept between forward and backward. Replaces the
+ * geomBuffer / imgBuffer / binningBuffer resize callbacks (RAST/rasterize_points.cu:27-35,
+ * required<T>() in RAST/cuda_rasterizer/rasterizer_impl.h). `R_cap` is the capacity, in
+ * (Gaussian,tile) instances, of the binning buffer: the reference sizes it after a blocking
+ * read-back of num_rendered (rasterizer_impl.cu:304); here the caller provides a capacity and
+ * the forward raises counters[RTG_CNT_OVERFLOW] (and renders nothing) if it was too small. */
+int rtg_splat_workspace_bytes(int32_t P, int32_t H, int32_t W, int64_t R_cap, size_t *geom_bytes, size_t *img_bytes,
+                              size_t *bin_bytes);
+
+/* Replaces CudaRasterizer::Rasterizer::forward (RAST/cuda_rasterizer/rasterizer.h:28-66,
+ * rasterizer_impl.cu:205-437) together with the output initialisation of
+ * RasterizeGaussiansCUDA (rasterize_points.cu:79-87): every element of every output is written.
+ * Exactly one of (shs | colors_precomp) and one of (scales+rotations | cov3D_precomp) must be
+ * non-NULL, as in GaussianRasterizer.forward (__init__.py:335-347). `M` = SH coefficients per
+ * Gaussian. `counters`: device, RTG_CNT_WORDS int32. `counters_host` (may be NULL): pinned, device-mapped
+ * host memory that receives a copy of the counters straight from the scan kernel; `scan_done_event` (may be
+ * NULL): a cudaEvent_t recorded right after that kernel, so a caller can learn num_rendered / overflow
+ * while the rest of the forward is still executing (the reference blocks the whole device instead,
+ * rasterizer_impl.cu:304,346). */
+int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+                      const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
+                      const float *cov3D_precomp, const int32_t *tile_mask, void *geom_ws, void *img_ws, void *bin_ws,
+                      int64_t R_cap, float *out_color, float *out_depth, int32_t *out_hit_color, int32_t *out_hit_depth,
+                      float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, int32_t *radii,
+                      int32_t *counters, int32_t *counters_host, void *scan_done_event, void *stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:68-105, rasterizer_impl.cu:441-560)
+ * and the zero-initialisation of RasterizeGaussiansBackwardCUDA (rasterize_points.cu:195-203):
+ * every element of every non-NULL gradient output is written. The three state buffers, `R_cap` and
+ * `counters` are those of the matching forward call; `final_T` is the forward's out_T,
+ * `hit_image` its out_hit_depth (__init__.py:172-235). `grad2d_scratch`: P*16 floats that must be
+ * all-zero on entry and are left all-zero on exit. Optional outputs (may be NULL):
+ * dL_dcolors_precomp, dL_dcov3D, dL_dmeans2D. */
+int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+                       const float *colors_precomp, const float *scales, const float *rotations,
+                       const float *cov3D_precomp, const int32_t *radii, const void *geom_ws, const void *img_ws,
+                       const void *bin_ws, int64_t R_cap, const int32_t *counters, const float *final_T, const int32_t *hit_image, const float *dL_dcolor,
+                       const float *dL_ddepth, float *grad2d_scratch, float *dL_dmeans3D, float *dL_dsh,
+                       float *dL_dcolors_precomp, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
+                       float *dL_dcov3D, float *dL_dmeans2D, void *stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:21-26, rasterizer_impl.cu:145-157). */
+int rtg_splat_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                           uint8_t *present, void *stream);
+
+/* ---- optimizer step ------------------------------------------------------------------------
+ * Replaces torch.optim.Adam(l, lr=0.0, eps=1e-15).step() over the parameter groups built by
+ * GaussianPointCloud.parametrize (SLAM/gaussian_pointcloud.py:245-284; SLAM/multiprocess/
+ * mapper.py:156,452): one launch for all groups, bias-corrected Adam, no weight decay, no amsgrad. */
+#define RTG_ADAM_MAX_GROUPS 8
+typedef struct RtgAdamGroup {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    int64_t numel;
+    float lr;
+    float _pad;
+} RtgAdamGroup;
+int rtg_adam_step(const RtgAdamGroup *groups, int32_t n_groups, float beta1, float beta2, float eps, int32_t step,
+                  void *stream);
+
+/* ---- projective point-to-plane ICP ---------------------------------------------------------
+ * Pyramid level: replaces nn.MaxPool2d(pool) (SLAM/icp.py:343-345,374) + compute_vertex_map
+ * (SLAM/utils.py:65-75) + compute_normal_map (SLAM/utils.py:100-122). `depth`: (H,W) full
+ * resolution; outputs (H/pool, W/pool, 3) channels-last. fx..cy are the level intrinsics
+ * (K*downscale, SLAM/utils.py:517-519). `ws`: rtg_icp_workspace_bytes() bytes. */
+size_t rtg_icp_workspace_bytes(int32_t H, int32_t W);
+int rtg_icp_build_level(const float *depth, int32_t H, int32_t W, int32_t pool, float fx, float fy, float cx, float cy,
+                        float *vertex_out, float *normal_out, void *ws, void *stream);
+
+/* `iters` Gauss-Newton iterations on one level: replaces the loop of ICP.icp (SLAM/icp.py:33-48):
+ * compute_residuals_jacobian (:52-104), compute_jtj/jtr (:107-119), lev_mar_H (:248),
+ * least_square_solve/invH (:313-333), exp_se3 (:271), forward_update_pose (:259). "0" is the
+ * current frame, "1" the previous/model frame, as inside icp(). `pose`: device, 16 floats
+ * row-major, updated in place. `valid_ratio`: device float (may be NULL). */
+int rtg_icp_solve_level(const float *vertex0, const float *normal0, const float *vertex1, const float *normal1,
+                        int32_t H, int32_t W, float fx, float fy, float cx, float cy, float distance_threshold,
+                        float normal_cos_threshold, float damping, int32_t iters, float *pose, float *valid_ratio,
+                        void *ws, void *stream);
+
+/* point2plane_loss(p_t0, p_t1 @ R^T + t, n_t0, "mean") (SLAM/icp.py:7-13,444-447); `loss`: device float. */
+int rtg_icp_point2plane_loss(const float *vertex_t0, const float *vertex_t1, const float *normal_t0, int32_t H, int32_t W,
+                             const float *pose, float *loss, void *ws, void *stream);
+
+/* IcpTracker.update_last_status depth filling (SLAM/icp.py:397-415): in place on render_depth. */
+int rtg_icp_fill_model_depth(float *render_depth, const float *frame_depth, const float *render_normal,
+                             const float *frame_normal, int32_t H, int32_t W, float distance_threshold,
+                             float normal_threshold, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTG_SPLAT_B200_H */

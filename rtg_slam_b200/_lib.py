@@ -1,0 +1,90 @@
+"""ctypes binding of librtg_splat_b200.so (the C ABI declared in include/rtg_splat_b200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librtg_splat_b200.so")
+
+RTG_CNT_WORDS = 8
+RTG_ADAM_MAX_GROUPS = 8
+
+
+class RtgSplatView(C.Structure):
+    _fields_ = [
+        ("image_height", C.c_int32), ("image_width", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+        ("cx", C.c_float), ("cy", C.c_float),
+        ("scale_modifier", C.c_float), ("color_sigma", C.c_float),
+        ("opaque_threshold", C.c_float), ("depth_threshold", C.c_float),
+        ("normal_threshold", C.c_float), ("T_threshold", C.c_float),
+        ("sh_degree", C.c_int32), ("prefiltered", C.c_int32),
+        ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("bg", C.c_void_p),
+    ]
+
+
+class RtgAdamGroup(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("numel", C.c_int64), ("lr", C.c_float), ("_pad", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/rtg_splat_b200.h
+_VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SIGNATURES = {
+    "rtg_last_error": (C.c_char_p, []),
+    "rtg_version": (C.c_int, []),
+    "rtg_splat_workspace_bytes": (C.c_int, [_I32, _I32, _I32, _I64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "rtg_splat_forward": (C.c_int, [C.POINTER(RtgSplatView), _I32, _I32] + [_VP] * 8 + [_VP, _VP, _VP, _I64] + [_VP] * 8 + [_VP, _VP, _VP, _VP]),
+    "rtg_splat_backward": (C.c_int, [C.POINTER(RtgSplatView), _I32, _I32] + [_VP] * 6 + [_VP, _VP, _VP, _VP, _I64, _VP] + [_VP] * 4 + [_VP] + [_VP] * 8 + [_VP]),
+    "rtg_splat_mark_visible": (C.c_int, [_I32, _VP, _VP, _VP, _VP, _VP]),
+    "rtg_adam_step": (C.c_int, [C.POINTER(RtgAdamGroup), _I32, _F, _F, _F, _I32, _VP]),
+    "rtg_icp_workspace_bytes": (C.c_size_t, [_I32, _I32]),
+    "rtg_icp_build_level": (C.c_int, [_VP, _I32, _I32, _I32, _F, _F, _F, _F, _VP, _VP, _VP, _VP]),
+    "rtg_icp_solve_level": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _F, _F, _F, _F, _F, _I32, _VP, _VP, _VP, _VP]),
+    "rtg_icp_point2plane_loss": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "rtg_icp_fill_model_depth": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _VP]),
+}
+
+_lib = None
+
+
+class RtgError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the shared library (building is __graft_entry__.build()'s job, not done implicitly here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RtgError(
+            f"{LIB_PATH} is missing: the sm_100a extension has not been built. Run `python -m rtg_slam_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU or PyTorch fallback for this path.")
+    h = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(h, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = h
+    return h
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().rtg_last_error()
+        raise RtgError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def header_symbols():
+    """Names of all functions declared in include/rtg_splat_b200.h (used by the ABI test)."""
+    import re
+    hdr = os.path.join(HERE, "..", "include", "rtg_splat_b200.h")
+    txt = open(hdr).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtg_[a-z0-9_]+)\s*\(", txt)))

@@ -1,0 +1,197 @@
+// Per-tile bucketing of (Gaussian, tile) instances without any host round trip.
+//
+// The reference emits (tile<<32 | depth) keys after a device-wide prefix sum over Gaussians, reads
+// the instance count back to the host, runs a device-wide 64-bit radix sort, and compacts the
+// non-empty tiles on the CPU (RAST/cuda_rasterizer/rasterizer_impl.cu:300-362). Here the tile
+// histogram comes out of the preprocess pass, one small scan turns it into tile offsets (and into
+// the ascending list of non-empty tiles), instances are scattered straight into their tile's
+// bucket, and each bucket is depth-sorted on chip. Sorting by (depth bits, Gaussian id) reproduces
+// the order of the reference's stable sort, whose ties are broken by emission (= Gaussian) order.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rtg {
+
+// ---------------------------------------------------------------- tile scan (single CTA)
+__global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long long R_cap, int *__restrict__ counters,
+                                                         int *__restrict__ counters_host) {
+    __shared__ uint32_t s_warp[32], s_warp_act[32];
+    __shared__ uint32_t s_carry, s_carry_act, s_max;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_carry = 0; s_carry_act = 0; s_max = 0; }
+    __syncthreads();
+    uint32_t local_max = 0;
+    for (int base = 0; base < T; base += 1024) {
+        const int i = base + tid;
+        const uint32_t c = (i < T) ? b.tile_count[i] : 0u;
+        const uint32_t a = c > 0 ? 1u : 0u;
+        local_max = max(local_max, c);
+        uint32_t v = c, va = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, o), na = __shfl_up_sync(0xffffffffu, va, o);
+            if (lane >= o) { v += n; va += na; }
+        }
+        if (lane == 31) { s_warp[wid] = v; s_warp_act[wid] = va; }
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane], wa = s_warp_act[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, w, o), na = __shfl_up_sync(0xffffffffu, wa, o);
+                if (lane >= o) { w += n; wa += na; }
+            }
+            s_warp[lane] = w; s_warp_act[lane] = wa;
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry, carry_a = s_carry_act;
+        const uint32_t incl = v + (wid > 0 ? s_warp[wid - 1] : 0u) + carry;
+        const uint32_t incl_a = va + (wid > 0 ? s_warp_act[wid - 1] : 0u) + carry_a;
+        if (i < T) {
+            b.tile_offset[i] = incl - c;
+            if (a) b.active[incl_a - 1] = (uint32_t)i;
+        }
+        __syncthreads();
+        if (tid == 1023) { s_carry = incl; s_carry_act = incl_a; }
+        __syncthreads();
+    }
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 16));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 8));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 4));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 2));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 1));
+    if (lane == 0) atomicMax(&s_max, local_max);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t R = s_carry;
+        b.tile_offset[T] = R;
+        counters[0] = (int)R;
+        counters[1] = (int)s_carry_act;
+        counters[2] = ((long long)R > R_cap) ? 1 : 0;
+        counters[3] = (int)s_max;
+        if (counters_host) {
+            counters_host[0] = (int)R;
+            counters_host[1] = (int)s_carry_act;
+            counters_host[2] = ((long long)R > R_cap) ? 1 : 0;
+            counters_host[3] = (int)s_max;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- scatter into tile buckets
+__global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P, const GeomState g, const int *__restrict__ radii,
+                                                      const int *__restrict__ tile_mask, BinState b, long long R_cap,
+                                                      const int *__restrict__ counters) {
+    if (counters[2]) return;  // capacity overflow: render nothing, the caller retries with a larger buffer
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const int r = radii[idx];
+    if (r <= 0) return;
+    int x0, y0, x1, y1;
+    tile_rect(g.xy[idx], r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
+    const uint64_t key = ((uint64_t)__float_as_uint(g.depth[idx]) << 32) | (uint32_t)idx;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+            const int t = y * vp.tiles_x + x;
+            if (__ldg(tile_mask + t)) {
+                const uint32_t pos = b.tile_offset[t] + atomicAdd(b.tile_fill + t, 1u);
+                b.keys[pos] = key;
+            }
+        }
+}
+
+// ---------------------------------------------------------------- per-tile depth sort
+#define SORT_THREADS 256
+#define SORT_SMEM_KEYS 4096
+
+__device__ __forceinline__ void bitonic_sort(uint64_t *k, const int N, const int tid, const int nthreads) {
+    for (int size = 2; size <= N; size <<= 1) {
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < (N >> 1); i += nthreads) {
+                const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int c = a | j;
+                const bool up = ((a & size) == 0);
+                const uint64_t x = k[a], y = k[c];
+                if ((x > y) == up) { k[a] = y; k[c] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int n) {
+    int N = 1;
+    while (N < n) N <<= 1;
+    return N;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(BinState b, const int *__restrict__ counters) {
+    __shared__ uint64_t s_keys[SORT_SMEM_KEYS];
+    if (counters[2]) return;
+    const int nact = counters[1];
+    for (int ai = blockIdx.x; ai < nact; ai += gridDim.x) {
+        const uint32_t tile = b.active[ai];
+        const uint32_t start = b.tile_offset[tile];
+        const int n = (int)(b.tile_offset[tile + 1] - start);
+        uint64_t *gk = b.keys + start;
+        uint32_t *out = b.point_list + start;
+        if (n <= SORT_SMEM_KEYS) {
+            const int N = next_pow2(n);
+            for (int i = threadIdx.x; i < N; i += SORT_THREADS) s_keys[i] = (i < n) ? gk[i] : 0xffffffffffffffffull;
+            __syncthreads();
+            bitonic_sort(s_keys, N, threadIdx.x, SORT_THREADS);
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS) out[i] = (uint32_t)s_keys[i];
+            __syncthreads();
+        } else {
+            // Rare oversized bucket: sort in place in global memory (L2-resident). Elements past n of
+            // the padded power-of-two network are virtual +inf keys: a compare-exchange whose upper
+            // index is >= n can only matter when ascending (never moves +inf down) ...
+            // To stay simple and exact, run an odd-even merge on chunks instead:
+            //   1) sort chunks of SORT_SMEM_KEYS on chip, 2) merge chunks pairwise via rank computation.
+            const int nchunks = (n + SORT_SMEM_KEYS - 1) / SORT_SMEM_KEYS;
+            for (int c = 0; c < nchunks; c++) {
+                const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);
+                const int N = next_pow2(cn);
+                for (int i = threadIdx.x; i < N; i += SORT_THREADS) s_keys[i] = (i < cn) ? gk[c0 + i] : 0xffffffffffffffffull;
+                __syncthreads();
+                bitonic_sort(s_keys, N, threadIdx.x, SORT_THREADS);
+                for (int i = threadIdx.x; i < cn; i += SORT_THREADS) gk[c0 + i] = s_keys[i];
+                __syncthreads();
+            }
+            // rank of every key among all chunks = sum over chunks of (#keys smaller); keys are unique
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+                const uint64_t key = gk[i];
+                int rank = 0;
+                for (int c = 0; c < nchunks; c++) {
+                    const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);
+                    int lo = 0, hi = cn;  // first index with gk[c0+idx] >= key
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (gk[c0 + mid] < key) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo;
+                }
+                out[rank] = (uint32_t)key;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+void launch_tile_scan(const BinState &b, int T, int64_t R_cap, int32_t *counters, int32_t *counters_host, cudaStream_t s) {
+    tile_scan_kernel<<<1, 1024, 0, s>>>(b, T, (long long)R_cap, counters, counters_host);
+}
+
+void launch_scatter(const ViewParams &vp, int P, const GeomState &g, const int *radii, const int *tile_mask, const BinState &b,
+                    int64_t R_cap, const int32_t *counters, cudaStream_t s) {
+    if (P <= 0) return;
+    scatter_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, g, radii, tile_mask, b, (long long)R_cap, counters);
+}
+
+void launch_tile_sort(const BinState &b, int T, const int32_t *counters, cudaStream_t s) {
+    if (T <= 0) return;
+    tile_sort_kernel<<<T, SORT_THREADS, 0, s>>>(b, counters);
+}
+
+}  // namespace rtg

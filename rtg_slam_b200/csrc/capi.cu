@@ -1,0 +1,240 @@
+// C ABI of librtg_splat_b200.so -- see include/rtg_splat_b200.h for the contract of every entry point.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+
+#include "../../include/rtg_splat_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rtg {
+int launch_adam(const RtgAdamGroup *groups, int n_groups, float beta1, float beta2, float eps, int step, cudaStream_t s);
+size_t icp_ws_bytes();
+void launch_icp_build_level(const float *depth, int H, int W, int pool, float fx, float fy, float cx, float cy, float *vertex,
+                            float *normal, void *ws, cudaStream_t s);
+void launch_icp_solve_level(const float *v0, const float *n0, const float *v1, const float *n1, int H, int W, float fx, float fy,
+                            float cx, float cy, float dist_thr, float cos_thr, float damping, int iters, float *pose,
+                            float *valid_ratio, void *ws, cudaStream_t s);
+void launch_icp_p2p(const float *v_t0, const float *v_t1, const float *n_t0, int H, int W, const float *pose, float *loss,
+                    void *ws, cudaStream_t s);
+void launch_icp_fill(float *render_depth, const float *frame_depth, const float *rn, const float *fn, int H, int W, float dthr,
+                     float nthr, cudaStream_t s);
+}  // namespace rtg
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+static int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return RTG_OK;
+}
+
+static rtg::ViewParams make_view(const RtgSplatView *v) {
+    rtg::ViewParams p;
+    p.H = v->image_height;
+    p.W = v->image_width;
+    p.tiles_x = (p.W + RTG_TILE - 1) / RTG_TILE;
+    p.tiles_y = (p.H + RTG_TILE - 1) / RTG_TILE;
+    p.tanfovx = v->tanfovx;
+    p.tanfovy = v->tanfovy;
+    // rasterizer_impl.cu:244-245
+    p.focal_y = p.H / (2.0f * v->tanfovy);
+    p.focal_x = p.W / (2.0f * v->tanfovx);
+    p.cx = v->cx;
+    p.cy = v->cy;
+    p.scale_modifier = v->scale_modifier;
+    p.color_sigma = v->color_sigma;
+    p.opaque_thr = v->opaque_threshold;
+    p.depth_thr = v->depth_threshold;
+    p.normal_thr = v->normal_threshold;
+    p.T_thr = v->T_threshold;
+    p.sh_degree = v->sh_degree;
+    p.prefiltered = v->prefiltered;
+    p.view = v->viewmatrix;
+    p.proj = v->projmatrix;
+    p.campos = v->campos;
+    p.bg = v->bg;
+    return p;
+}
+
+extern "C" {
+
+const char *rtg_last_error(void) { return g_err.c_str(); }
+int rtg_version(void) { return 100; }
+
+int rtg_splat_workspace_bytes(int32_t P, int32_t H, int32_t W, int64_t R_cap, size_t *geom_bytes, size_t *img_bytes,
+                              size_t *bin_bytes) {
+    if (P < 0 || H <= 0 || W <= 0 || R_cap < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_workspace_bytes: bad sizes");
+    const size_t T = (size_t)((W + RTG_TILE - 1) / RTG_TILE) * ((H + RTG_TILE - 1) / RTG_TILE);
+    size_t g = 0, i = 0, b = 0;
+    rtg::geom_from(nullptr, (size_t)P, &g);
+    rtg::img_from(nullptr, (size_t)H * W, &i);
+    rtg::bin_from(nullptr, T, (size_t)R_cap, &b);
+    if (geom_bytes) *geom_bytes = g + 256;
+    if (img_bytes) *img_bytes = i + 256;
+    if (bin_bytes) *bin_bytes = b + 256;
+    return RTG_OK;
+}
+
+static int validate_view(const RtgSplatView *v, const char *who) {
+    if (!v) return fail(RTG_ERR_INVALID_ARGUMENT, std::string(who) + ": view is NULL");
+    if (v->image_height <= 0 || v->image_width <= 0) return fail(RTG_ERR_INVALID_ARGUMENT, std::string(who) + ": bad image size");
+    if (!v->viewmatrix || !v->projmatrix || !v->campos || !v->bg)
+        return fail(RTG_ERR_INVALID_ARGUMENT, std::string(who) + ": view matrices / campos / bg must be device pointers");
+    if (v->sh_degree < 0 || v->sh_degree > 3) return fail(RTG_ERR_INVALID_ARGUMENT, std::string(who) + ": sh_degree must be 0..3");
+    return RTG_OK;
+}
+
+int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+                      const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
+                      const float *cov3D_precomp, const int32_t *tile_mask, void *geom_ws, void *img_ws, void *bin_ws,
+                      int64_t R_cap, float *out_color, float *out_depth, int32_t *out_hit_color, int32_t *out_hit_depth,
+                      float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *counters,
+                      int32_t *counters_host, void *scan_done_event, void *stream) {
+    int rc = validate_view(view, "rtg_splat_forward");
+    if (rc) return rc;
+    if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: P < 0");
+    if (!out_color || !out_depth || !out_hit_color || !out_hit_depth || !out_hit_color_weight || !out_hit_depth_weight || !out_T ||
+        !counters || !geom_ws || !img_ws || !bin_ws || !tile_mask)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: NULL output / workspace / tile_mask pointer");
+    if (P > 0) {
+        if (!means3D || !opacities || !radii) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: NULL means3D / opacities / radii");
+        // same exactly-one-of rules as GaussianRasterizer.forward (__init__.py:335-347)
+        if ((shs == nullptr) == (colors_precomp == nullptr))
+            return fail(RTG_ERR_INVALID_ARGUMENT, "Please provide excatly one of either SHs or precomputed colors!");
+        if (((scales == nullptr || rotations == nullptr) && cov3D_precomp == nullptr) ||
+            ((scales != nullptr || rotations != nullptr) && cov3D_precomp != nullptr))
+            return fail(RTG_ERR_INVALID_ARGUMENT,
+                        "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        if (shs && (M < (view->sh_degree + 1) * (view->sh_degree + 1) || M > 16))
+            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: M must hold (sh_degree+1)^2 coefficients and be <= 16");
+        if ((((uintptr_t)rotations) & 15) || (M == 16 && (((uintptr_t)shs) & 15)))
+            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: rotations / shs must be 16-byte aligned");
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const rtg::ViewParams vp = make_view(view);
+    const int T = vp.tiles_x * vp.tiles_y;
+    rtg::GeomState g = rtg::geom_from(geom_ws, (size_t)P);
+    rtg::ImgState img = rtg::img_from(img_ws, (size_t)vp.H * vp.W);
+    rtg::BinState b = rtg::bin_from(bin_ws, (size_t)T, (size_t)R_cap);
+
+    // tile_count and tile_fill are adjacent (bin_from): one clear
+    cudaError_t e = cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)b.tile_offset - (char *)b.tile_count), s);
+    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward memset: ") + cudaGetErrorString(e));
+    rtg::launch_preprocess_fwd(vp, P, M, means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp, tile_mask, g,
+                               radii, b.tile_count, s);
+    rtg::launch_tile_scan(b, T, R_cap, counters, counters_host, s);
+    if (scan_done_event) {
+        e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(scan_done_event), s);
+        if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward event: ") + cudaGetErrorString(e));
+    }
+    rtg::launch_scatter(vp, P, g, radii, tile_mask, b, R_cap, counters, s);
+    rtg::launch_tile_sort(b, T, counters, s);
+    rtg::launch_render_fwd(vp, g, b, img, counters, out_color, out_depth, out_hit_color, out_hit_depth, out_hit_color_weight,
+                           out_hit_depth_weight, out_T, s);
+    return check_launch("rtg_splat_forward");
+}
+
+int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+                       const float *colors_precomp, const float *scales, const float *rotations, const float *cov3D_precomp,
+                       const int32_t *radii, const void *geom_ws, const void *img_ws, const void *bin_ws, int64_t R_cap,
+                       const int32_t *counters, const float *final_T, const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch,
+                       float *dL_dmeans3D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity, float *dL_dscales,
+                       float *dL_drotations, float *dL_dcov3D, float *dL_dmeans2D, void *stream) {
+    int rc = validate_view(view, "rtg_splat_backward");
+    if (rc) return rc;
+    if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: P < 0");
+    if (P == 0) return RTG_OK;
+    if (!means3D || !radii || !geom_ws || !img_ws || !bin_ws || !counters || !final_T || !hit_image || !dL_dcolor || !dL_ddepth ||
+        !grad2d_scratch || !dL_dmeans3D || !dL_dopacity)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: NULL pointer");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "Please provide excatly one of either SHs or precomputed colors!");
+    if (shs && !dL_dsh) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: dL_dsh is NULL");
+    if (colors_precomp && !dL_dcolors_precomp) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: dL_dcolors_precomp is NULL");
+    if (cov3D_precomp == nullptr && (!scales || !rotations || !dL_dscales || !dL_drotations))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: scales / rotations and their gradients are required");
+    if (cov3D_precomp != nullptr && !dL_dcov3D) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: dL_dcov3D is NULL");
+    if ((((uintptr_t)grad2d_scratch) & 15) || (((uintptr_t)dL_drotations) & 15) || (M == 16 && (((uintptr_t)dL_dsh) & 15)))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: scratch / dL_drotations / dL_dsh must be 16-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const rtg::ViewParams vp = make_view(view);
+    const int T = vp.tiles_x * vp.tiles_y;
+    rtg::GeomState g = rtg::geom_from(const_cast<void *>(geom_ws), (size_t)P);
+    rtg::ImgState img = rtg::img_from(const_cast<void *>(img_ws), (size_t)vp.H * vp.W);
+    rtg::BinState b = rtg::bin_from(const_cast<void *>(bin_ws), (size_t)T, (size_t)R_cap);
+    // counters live in the scan output: recompute the overflow word location is not needed -- the
+    // backward reads the same device counters the forward wrote.
+    rtg::launch_render_bwd(vp, g, b, img, counters, means3D, scales, rotations, final_T, hit_image, dL_dcolor, dL_ddepth,
+                           grad2d_scratch, s);
+    rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, radii, g, grad2d_scratch, dL_dmeans3D,
+                               dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, s);
+    return check_launch("rtg_splat_backward");
+}
+
+int rtg_splat_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,
+                           void *stream) {
+    if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_mark_visible: P < 0");
+    if (P == 0) return RTG_OK;
+    if (!means3D || !viewmatrix || !projmatrix || !present) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_mark_visible: NULL pointer");
+    rtg::launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_splat_mark_visible");
+}
+
+int rtg_adam_step(const RtgAdamGroup *groups, int32_t n_groups, float beta1, float beta2, float eps, int32_t step, void *stream) {
+    if (!groups || n_groups <= 0 || n_groups > RTG_ADAM_MAX_GROUPS) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_adam_step: bad groups");
+    if (step < 1) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_adam_step: step must be >= 1");
+    for (int i = 0; i < n_groups; i++)
+        if (groups[i].grad && (!groups[i].param || !groups[i].exp_avg || !groups[i].exp_avg_sq))
+            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_adam_step: NULL param / state pointer");
+    rtg::launch_adam(groups, n_groups, beta1, beta2, eps, step, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_adam_step");
+}
+
+size_t rtg_icp_workspace_bytes(int32_t H, int32_t W) {
+    (void)H; (void)W;
+    return rtg::icp_ws_bytes();
+}
+
+int rtg_icp_build_level(const float *depth, int32_t H, int32_t W, int32_t pool, float fx, float fy, float cx, float cy,
+                        float *vertex_out, float *normal_out, void *ws, void *stream) {
+    if (!depth || !vertex_out || !normal_out || !ws || H <= 0 || W <= 0 || pool < 1 || H / pool < 1 || W / pool < 1)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_build_level: bad arguments");
+    rtg::launch_icp_build_level(depth, H, W, pool, fx, fy, cx, cy, vertex_out, normal_out, ws, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_icp_build_level");
+}
+
+int rtg_icp_solve_level(const float *vertex0, const float *normal0, const float *vertex1, const float *normal1, int32_t H, int32_t W,
+                        float fx, float fy, float cx, float cy, float distance_threshold, float normal_cos_threshold, float damping,
+                        int32_t iters, float *pose, float *valid_ratio, void *ws, void *stream) {
+    if (!vertex0 || !normal0 || !vertex1 || !normal1 || !pose || !ws || H <= 0 || W <= 0 || iters < 0)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_solve_level: bad arguments");
+    rtg::launch_icp_solve_level(vertex0, normal0, vertex1, normal1, H, W, fx, fy, cx, cy, distance_threshold, normal_cos_threshold,
+                                damping, iters, pose, valid_ratio, ws, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_icp_solve_level");
+}
+
+int rtg_icp_point2plane_loss(const float *vertex_t0, const float *vertex_t1, const float *normal_t0, int32_t H, int32_t W,
+                             const float *pose, float *loss, void *ws, void *stream) {
+    if (!vertex_t0 || !vertex_t1 || !normal_t0 || !pose || !loss || !ws || H <= 0 || W <= 0)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_point2plane_loss: bad arguments");
+    rtg::launch_icp_p2p(vertex_t0, vertex_t1, normal_t0, H, W, pose, loss, ws, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_icp_point2plane_loss");
+}
+
+int rtg_icp_fill_model_depth(float *render_depth, const float *frame_depth, const float *render_normal, const float *frame_normal,
+                             int32_t H, int32_t W, float distance_threshold, float normal_threshold, void *stream) {
+    if (!render_depth || !frame_depth || !render_normal || !frame_normal || H <= 0 || W <= 0)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_fill_model_depth: bad arguments");
+    rtg::launch_icp_fill(render_depth, frame_depth, render_normal, frame_normal, H, W, distance_threshold, normal_threshold,
+                         reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_icp_fill_model_depth");
+}
+
+}  // extern "C"

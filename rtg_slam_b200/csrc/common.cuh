@@ -1,0 +1,143 @@
+// Shared definitions of the sm_100a splat kernels. Product code: never includes or calls oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define RTG_TILE 16
+#define RTG_TILE_PIX 256
+#define RTG_REC 16  // floats per Gaussian in the 2-D gradient record
+
+namespace rtg {
+
+// Gradient record slots (one 64-byte line per Gaussian, filled by render-backward atomics,
+// consumed and cleared by preprocess-backward).
+enum { REC_COLOR = 0, REC_MEAN2D = 3, REC_CONIC = 5, REC_OPACITY = 8, REC_DMEAN = 9, REC_DROT = 12 };
+
+struct ViewParams {
+    int H, W, tiles_x, tiles_y;
+    float tanfovx, tanfovy, focal_x, focal_y, cx, cy;
+    float scale_modifier, color_sigma, opaque_thr, depth_thr, normal_thr, T_thr;
+    int sh_degree, prefiltered;
+    const float *view, *proj, *campos, *bg;
+};
+
+// Per-Gaussian state written by the forward preprocess (SoA, 16-byte records so that every
+// gather in the render kernels is one LDG.128).
+struct GeomState {
+    float *depth;          // [P]   view-space z
+    float2 *xy;            // [P]   pixel-space centre
+    float4 *conic_opacity; // [P]   inverse 2-D covariance (a,b,c) + opacity
+    float4 *rgb_flags;     // [P]   SH colour (clamped at 0) + clamp bits (int in .w)
+    float4 *hit0;          // [P]   view-space normal (xyz) + scale_max*scale_modifier
+    float4 *hit1;          // [P]   view-space centre (xyz) + normal axis (int in .w)
+};
+
+struct BinState {
+    uint32_t *tile_count;  // [T]   instances per tile
+    uint32_t *tile_fill;   // [T]   scatter cursors
+    uint32_t *tile_offset; // [T+1] exclusive scan of tile_count
+    uint32_t *active;      // [T]   ascending ids of tiles with a non-empty list
+    uint64_t *keys;        // [R_cap] (depth bits << 32 | gaussian id), bucketed by tile
+    uint32_t *point_list;  // [R_cap] gaussian ids, per tile front-to-back
+};
+
+struct ImgState {
+    uint32_t *n_contrib; // [H*W]
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+static inline T *carve(char *&p, size_t n) {
+    T *r = reinterpret_cast<T *>(p);
+    p += align_up(n * sizeof(T), 256);
+    return r;
+}
+
+static inline GeomState geom_from(void *ws, size_t P, size_t *bytes = nullptr) {
+    char *p = reinterpret_cast<char *>(ws);
+    GeomState g;
+    g.depth = carve<float>(p, P);
+    g.xy = carve<float2>(p, P);
+    g.conic_opacity = carve<float4>(p, P);
+    g.rgb_flags = carve<float4>(p, P);
+    g.hit0 = carve<float4>(p, P);
+    g.hit1 = carve<float4>(p, P);
+    if (bytes) *bytes = (size_t)(p - reinterpret_cast<char *>(ws));
+    return g;
+}
+
+static inline BinState bin_from(void *ws, size_t T, size_t R_cap, size_t *bytes = nullptr) {
+    char *p = reinterpret_cast<char *>(ws);
+    BinState b;
+    // tile_count and tile_fill are adjacent: one memset clears both
+    b.tile_count = carve<uint32_t>(p, T);
+    b.tile_fill = carve<uint32_t>(p, T);
+    b.tile_offset = carve<uint32_t>(p, T + 1);
+    b.active = carve<uint32_t>(p, T);
+    b.keys = carve<uint64_t>(p, R_cap);
+    b.point_list = carve<uint32_t>(p, R_cap);
+    if (bytes) *bytes = (size_t)(p - reinterpret_cast<char *>(ws));
+    return b;
+}
+
+static inline ImgState img_from(void *ws, size_t N, size_t *bytes = nullptr) {
+    char *p = reinterpret_cast<char *>(ws);
+    ImgState s;
+    s.n_contrib = carve<uint32_t>(p, N);
+    if (bytes) *bytes = (size_t)(p - reinterpret_cast<char *>(ws));
+    return s;
+}
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ float3 xform4x3(const float3 p, const float *m) {
+    return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ float4 xform4x4(const float3 p, const float *m) {
+    return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14], m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+__device__ __forceinline__ float3 xvec4x3(const float3 p, const float *m) {
+    return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z, m[1] * p.x + m[5] * p.y + m[9] * p.z,
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z);
+}
+__device__ __forceinline__ float3 xvec4x3T(const float3 p, const float *m) {
+    return make_float3(m[0] * p.x + m[1] * p.y + m[2] * p.z, m[4] * p.x + m[5] * p.y + m[6] * p.z,
+                       m[8] * p.x + m[9] * p.y + m[10] * p.z);
+}
+__device__ __forceinline__ int arg_max3(float a, float b, float c) { return (a >= b && a >= c) ? 0 : ((b >= a && b >= c) ? 1 : 2); }
+__device__ __forceinline__ int arg_min3(float a, float b, float c) { return (a <= b && a <= c) ? 0 : ((b <= a && b <= c) ? 1 : 2); }
+
+// Tile rectangle touched by a splat of integer radius r centred at p (same rounding as the
+// reference's getRect, auxiliary.h:49-57).
+__device__ __forceinline__ void tile_rect(const float2 p, int r, int gx, int gy, int &x0, int &y0, int &x1, int &y1) {
+    x0 = min(gx, max(0, (int)((p.x - r) / RTG_TILE)));
+    y0 = min(gy, max(0, (int)((p.y - r) / RTG_TILE)));
+    x1 = min(gx, max(0, (int)((p.x + r + RTG_TILE - 1) / RTG_TILE)));
+    y1 = min(gy, max(0, (int)((p.y + r + RTG_TILE - 1) / RTG_TILE)));
+}
+
+// Unit view ray through integer pixel (px,py) (ndc2ray, forward.cu:92-100).
+__device__ __forceinline__ float3 pixel_ray(int px, int py, float fx, float fy, float cx, float cy) {
+    float3 ray = make_float3(((float)px - cx) / fx, ((float)py - cy) / fy, 1.0f);
+    float n = 1.0f / sqrtf(ray.x * ray.x + ray.y * ray.y + ray.z * ray.z);
+    ray.x *= n; ray.y *= n; ray.z *= n;
+    return ray;
+}
+
+// Standard rotation matrix rows from a quaternion used as given (w,x,y,z); not re-normalised
+// (forward.cu:57,211).
+__device__ __forceinline__ void quat_to_R(const float4 q, float R[3][3]) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
+    R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
+    R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+}
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+#endif
+
+}  // namespace rtg

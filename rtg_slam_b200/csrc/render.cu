@@ -1,0 +1,400 @@
+// Tile compositing: forward colour + opaque-surfel depth, and the per-Gaussian backward.
+//
+// Semantics follow renderCUDA_withMask (RAST/cuda_rasterizer/forward.cu:636-861) and
+// renderCUDA_flat (backward.cu:808-1066). What differs by design:
+//  * one CTA per tile over a device-resident tile table (no host-side tile compaction); CTAs of
+//    empty / masked-out tiles write the reference's initial values (rasterize_points.cu:79-87);
+//  * the plane hit is evaluated lazily, only for the first entry with alpha >= opaque_threshold,
+//    from a per-Gaussian view-space record (the reference recomputes quaternion->normal and two
+//    4x3 transforms from global memory for every blended pair, forward.cu:778-790);
+//  * the backward walks only the prefix of the tile list that some pixel of the CTA actually
+//    blended, reduces the 9 per-pair gradient terms across the warp with a transposing butterfly
+//    (16 shuffles instead of 45) and issues one multi-lane atomic per (warp, Gaussian) into a
+//    64-byte gradient record, instead of 9 atomics per (pixel, Gaussian) pair;
+//  * hit_normal_c / hit_point_c are not stored per pixel: they are functions of the hit Gaussian
+//    and the pixel ray and are recomputed bit-identically in the backward.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rtg {
+
+#define BATCH 256
+
+__device__ __forceinline__ void pixel_of(const ViewParams &vp, int tile, int &px, int &py, bool &inside) {
+    const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+    px = tx * RTG_TILE + (threadIdx.x & 15);
+    py = ty * RTG_TILE + (threadIdx.x >> 4);
+    inside = px < vp.W && py < vp.H;
+}
+
+// Plane / centre depth of the first opaque entry (forward.cu:778-809). Returns depth; outputs the
+// distance tests so that the backward can re-take the same branch.
+__device__ __forceinline__ float surfel_depth(const float4 h0, const float4 h1, const float3 ray, float center_depth,
+                                              float depth_thr, float normal_thr, bool &plane) {
+    const float3 nc = make_float3(h0.x, h0.y, h0.z);
+    const float3 pc = make_float3(h1.x, h1.y, h1.z);
+    const float num = pc.x * nc.x + pc.y * nc.y + pc.z * nc.z;
+    const float den = ray.x * nc.x + ray.y * nc.y + ray.z * nc.z;
+    // the reference adds a double literal here: (float / (float + 1e-8)) is evaluated in double
+    const float t = (float)((double)num / ((double)den + 1e-8));
+    const float hz = t * ray.z;
+    const float angle_distance = fabsf(den);
+    const float depth_distance = fabsf(hz - pc.z);
+    plane = (depth_distance <= h0.w * depth_thr) && (angle_distance >= normal_thr);
+    return plane ? hz : center_depth;
+}
+
+__global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, const GeomState g, const BinState b, ImgState img,
+                                                         const int *__restrict__ counters, float *__restrict__ out_color,
+                                                         float *__restrict__ out_depth, int *__restrict__ out_hit_color,
+                                                         int *__restrict__ out_hit_depth, float *__restrict__ out_hcw,
+                                                         float *__restrict__ out_hdw, float *__restrict__ out_T) {
+    __shared__ int s_id[BATCH];
+    __shared__ float2 s_xy[BATCH];
+    __shared__ float4 s_co[BATCH];
+    __shared__ float4 s_rgb[BATCH];
+
+    const int tile = blockIdx.x;
+    int px, py;
+    bool inside;
+    pixel_of(vp, tile, px, py, inside);
+    const int pix_id = vp.W * py + px;
+    const int N = vp.H * vp.W;
+
+    const bool overflow = counters[2] != 0;
+    const uint32_t start = b.tile_offset[tile];
+    const int n = overflow ? 0 : (int)(b.tile_offset[tile + 1] - start);
+    if (n == 0) {
+        if (inside) {
+            out_color[pix_id] = 0.f; out_color[N + pix_id] = 0.f; out_color[2 * N + pix_id] = 0.f;
+            out_depth[pix_id] = 0.f;
+            out_hit_color[pix_id] = 0; out_hit_depth[pix_id] = 0;
+            out_hcw[pix_id] = 0.f; out_hdw[pix_id] = 0.f;
+            out_T[pix_id] = 1.f;
+            img.n_contrib[pix_id] = 0u;
+        }
+        return;
+    }
+
+    const float2 pixf = make_float2((float)px, (float)py);
+    const float3 ray = pixel_ray(px, py, vp.focal_x, vp.focal_y, vp.cx, vp.cy);
+    bool done = !inside;
+
+    float T = 1.0f, end_T = 1.0f;
+    uint32_t contributor = 0, last_contributor = 0;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    float depth_ = 0.f;
+    bool hit = false;
+    int hit_id = -1, hit_color_id = -1;
+    float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
+
+    const int rounds = (n + BATCH - 1) / BATCH;
+    int toDo = n;
+    for (int i = 0; i < rounds; i++, toDo -= BATCH) {
+        if (__syncthreads_count(done) == BATCH) break;
+        const int progress = i * BATCH + threadIdx.x;
+        if (progress < n) {
+            const int id = (int)b.point_list[start + progress];
+            s_id[threadIdx.x] = id;
+            s_xy[threadIdx.x] = g.xy[id];
+            s_co[threadIdx.x] = g.conic_opacity[id];
+            s_rgb[threadIdx.x] = g.rgb_flags[id];
+        }
+        __syncthreads();
+        const int cnt = min(BATCH, toDo);
+        for (int j = 0; !done && j < cnt; j++) {
+            contributor++;
+            const float2 xy = s_xy[j];
+            const float dx = xy.x - pixf.x, dy = xy.y - pixf.y;
+            const float4 co = s_co[j];
+            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+            if (power > 0.0f) continue;
+            const float alpha = fminf(0.99f, co.w * expf(power));
+            if (alpha < 1.0f / 255.0f) continue;
+
+            if (!hit && alpha >= vp.opaque_thr) {
+                const int id = s_id[j];
+                bool plane;
+                depth_ = surfel_depth(g.hit0[id], g.hit1[id], ray, g.depth[id], vp.depth_thr, vp.normal_thr, plane);
+                hit_id = id;
+                hit_dw = alpha * T;
+                hit = true;
+            }
+            const float test_T = T * (1.f - alpha);
+            if (test_T < vp.T_thr && hit) {
+                done = true;
+                continue;
+            }
+            if (test_T >= vp.T_thr) {
+                const float cw = alpha * T;
+                const float4 c = s_rgb[j];
+                C0 += c.x * cw; C1 += c.y * cw; C2 += c.z * cw;
+                if (cw > cw_max) {
+                    cw_max = cw;
+                    hit_color_id = s_id[j];
+                    hit_cw = cw;
+                }
+                last_contributor = contributor;
+                end_T = test_T;
+            }
+            T = test_T;
+        }
+    }
+
+    if (inside) {
+        const float bg0 = __ldg(vp.bg), bg1 = __ldg(vp.bg + 1), bg2 = __ldg(vp.bg + 2);
+        out_color[pix_id] = C0 + T * bg0;
+        out_color[N + pix_id] = C1 + T * bg1;
+        out_color[2 * N + pix_id] = C2 + T * bg2;
+        out_depth[pix_id] = depth_;
+        out_hit_depth[pix_id] = hit_id;
+        out_hit_color[pix_id] = hit_color_id;
+        out_hcw[pix_id] = hit_cw;
+        out_hdw[pix_id] = hit_dw;
+        out_T[pix_id] = end_T;
+        img.n_contrib[pix_id] = last_contributor;
+    }
+}
+
+// ------------------------------------------------------------------ backward
+
+// Sum 16 per-lane values across the warp with a transposing butterfly: after the call, value k's
+// total sits in v[0] of lanes 2k and 2k+1.
+__device__ __forceinline__ void warp_transpose_reduce16(float v[16], const int lane) {
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float send = hi ? v[i] : v[i + 8];
+            const float keep = hi ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = hi ? v[i] : v[i + 4];
+            const float keep = hi ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float send = hi ? v[i] : v[i + 2];
+            const float keep = hi ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b, const ImgState img,
+                                                         const int *__restrict__ counters, const float *__restrict__ means,
+                                                         const float *__restrict__ scales, const float *__restrict__ rots,
+                                                         const float *__restrict__ final_T, const int *__restrict__ hit_image,
+                                                         const float *__restrict__ dL_dcolor, const float *__restrict__ dL_ddepth,
+                                                         float *__restrict__ rec) {
+    __shared__ int s_id[BATCH];
+    __shared__ float2 s_xy[BATCH];
+    __shared__ float4 s_co[BATCH];
+    __shared__ float4 s_rgb[BATCH];
+    __shared__ uint32_t s_max[8];
+
+    if (counters[2]) return;
+    const int tile = blockIdx.x;
+    const uint32_t start = b.tile_offset[tile];
+    const int n = (int)(b.tile_offset[tile + 1] - start);
+    if (n == 0) return;
+    int px, py;
+    bool inside;
+    pixel_of(vp, tile, px, py, inside);
+    const int pix_id = vp.W * py + px;
+    const int N = vp.H * vp.W;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float2 pixf = make_float2((float)px, (float)py);
+
+    const float T_final = inside ? final_T[pix_id] : 0.f;
+    float T = T_final;
+    const uint32_t last_contributor = inside ? img.n_contrib[pix_id] : 0u;
+    float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
+    if (inside) {
+        dLp0 = dL_dcolor[pix_id]; dLp1 = dL_dcolor[N + pix_id]; dLp2 = dL_dcolor[2 * N + pix_id];
+    }
+    const float bg0 = __ldg(vp.bg), bg1 = __ldg(vp.bg + 1), bg2 = __ldg(vp.bg + 2);
+    const float bg_dot_dpixel = bg0 * dLp0 + bg1 * dLp1 + bg2 * dLp2;
+
+    // only the first `m` entries of the list were blended by some pixel of this tile
+    uint32_t wmax = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_max[wid] = wmax;
+    __syncthreads();
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) m = max(m, s_max[w]);
+
+    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
+    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+    const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
+
+    const int rounds = ((int)m + BATCH - 1) / BATCH;
+    for (int i = 0; i < rounds; i++) {
+        __syncthreads();
+        const int progress = i * BATCH + threadIdx.x;  // position from the back of the prefix
+        if (progress < (int)m) {
+            const int id = (int)b.point_list[start + (m - 1 - progress)];
+            s_id[threadIdx.x] = id;
+            s_xy[threadIdx.x] = g.xy[id];
+            s_co[threadIdx.x] = g.conic_opacity[id];
+            s_rgb[threadIdx.x] = g.rgb_flags[id];
+        }
+        __syncthreads();
+        const int cnt = min(BATCH, (int)m - i * BATCH);
+        for (int j = 0; j < cnt; j++) {
+            const uint32_t pos = m - 1 - (uint32_t)(i * BATCH + j);  // 0-based list position == reference `contributor`
+            if (pos >= wmax) continue;                               // warp-uniform
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = 0.f;
+            bool active = pos < last_contributor;
+            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+            float4 co = s_co[j];
+            if (active) {
+                const float2 xy = s_xy[j];
+                dx = xy.x - pixf.x; dy = xy.y - pixf.y;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                active = !(power > 0.0f);
+                if (active) {
+                    G = expf(power);
+                    alpha = fminf(0.99f, co.w * G);
+                    active = !(alpha < 1.0f / 255.0f);
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) continue;
+            if (active) {
+                T = T / (1.f - alpha);
+                const float dch = alpha * T;
+                const float4 c = s_rgb[j];
+                float dL_dalpha;
+                accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0; lc0 = c.x;
+                accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1; lc1 = c.y;
+                accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2; lc2 = c.z;
+                dL_dalpha = (c.x - accum0) * dLp0;
+                dL_dalpha += (c.y - accum1) * dLp1;
+                dL_dalpha += (c.z - accum2) * dLp2;
+                v[REC_COLOR + 0] = dch * dLp0;
+                v[REC_COLOR + 1] = dch * dLp1;
+                v[REC_COLOR + 2] = dch * dLp2;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                const float dL_dG = co.w * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * co.x - gdy * co.y;
+                const float dG_ddely = -gdy * co.z - gdx * co.y;
+                v[REC_MEAN2D + 0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[REC_MEAN2D + 1] = dL_dG * dG_ddely * ddely_dy;
+                v[REC_CONIC + 0] = -0.5f * gdx * dx * dL_dG;
+                v[REC_CONIC + 1] = -0.5f * gdx * dy * dL_dG;
+                v[REC_CONIC + 2] = -0.5f * gdy * dy * dL_dG;
+                v[REC_OPACITY] = G * dL_dalpha;
+            }
+            warp_transpose_reduce16(v, lane);
+            const int slot = lane >> 1;
+            if ((lane & 1) == 0 && slot <= REC_OPACITY) atomicAdd(rec + (size_t)s_id[j] * RTG_REC + slot, v[0]);
+        }
+    }
+
+    // depth-hit gradient (backward.cu:997-1065)
+    if (inside) {
+        const int gid = hit_image[pix_id];
+        if (gid >= 0) {
+            const float3 ray = pixel_ray(px, py, vp.focal_x, vp.focal_y, vp.cx, vp.cy);
+            const float4 h0 = g.hit0[gid], h1 = g.hit1[gid];
+            const float3 nc = make_float3(h0.x, h0.y, h0.z);
+            const float3 pc = make_float3(h1.x, h1.y, h1.z);
+            const float3 sc = make_float3(scales[3 * (size_t)gid], scales[3 * (size_t)gid + 1], scales[3 * (size_t)gid + 2]);
+            const float scale_max = fmaxf(fmaxf(sc.x, sc.y), sc.z);  // no scale_modifier here (backward.cu:1009)
+            const float num = pc.x * nc.x + pc.y * nc.y + pc.z * nc.z;
+            const float ndotr = nc.x * ray.x + nc.y * ray.y + nc.z * ray.z;
+            const float t = (float)((double)num / ((double)ndotr + 1e-8));
+            const float hz = t * ray.z;
+            const float angle_distance = fabsf(ndotr);
+            const float depth_distance = fabsf(hz - pc.z);
+            const float dL_ddi = dL_ddepth[pix_id];
+            const float *vm = vp.view;
+            float *r = rec + (size_t)gid * RTG_REC;
+            if (depth_distance <= vp.depth_thr * scale_max && angle_distance >= vp.normal_thr) {
+                const float nr = (float)((double)ndotr + 1e-8);
+                const float inv_nr = 1.f / nr, inv_nr2 = inv_nr * inv_nr;
+                const float np_ = num;
+                const float dpx = ray.z * nc.x * inv_nr, dpy = ray.z * nc.y * inv_nr, dpz = ray.z * nc.z * inv_nr;
+                const float v0 = __ldg(vm + 0), v1 = __ldg(vm + 1), v2 = __ldg(vm + 2), v4 = __ldg(vm + 4), v5 = __ldg(vm + 5),
+                            v6 = __ldg(vm + 6), v8 = __ldg(vm + 8), v9 = __ldg(vm + 9), v10 = __ldg(vm + 10);
+                atomicAdd(r + REC_DMEAN + 0, dL_ddi * (dpx * v0 + dpy * v1 + dpz * v2));
+                atomicAdd(r + REC_DMEAN + 1, dL_ddi * (dpx * v4 + dpy * v5 + dpz * v6));
+                atomicAdd(r + REC_DMEAN + 2, dL_ddi * (dpx * v8 + dpy * v9 + dpz * v10));
+                const int axis = arg_min3(sc.x, sc.y, sc.z);
+                const float n1 = ray.z * (nr * pc.x - np_ * ray.x) * inv_nr2;
+                const float n2 = ray.z * (nr * pc.y - np_ * ray.y) * inv_nr2;
+                const float n3 = ray.z * (nr * pc.z - np_ * ray.z) * inv_nr2;
+                const float w1 = n1 * v0 + n2 * v1 + n3 * v2;
+                const float w2 = n1 * v4 + n2 * v5 + n3 * v6;
+                const float w3 = n1 * v8 + n2 * v9 + n3 * v10;
+                const float4 q = reinterpret_cast<const float4 *>(rots)[gid];
+                const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+                float d0[3], d1[3], d2[3], d3[3];  // d(normal)/dq_k (propagateRotationGrad, backward.cu:100-148)
+                if (axis == 0) {
+                    d0[0] = 0; d0[1] = 2 * q3; d0[2] = -2 * q2;
+                    d1[0] = 0; d1[1] = 2 * q2; d1[2] = 2 * q3;
+                    d2[0] = -4 * q2; d2[1] = 2 * q1; d2[2] = -2 * q0;
+                    d3[0] = -4 * q3; d3[1] = 2 * q0; d3[2] = 2 * q1;
+                } else if (axis == 1) {
+                    d0[0] = -2 * q3; d0[1] = 0; d0[2] = 2 * q1;
+                    d1[0] = 2 * q2; d1[1] = -4 * q1; d1[2] = 2 * q0;
+                    d2[0] = 2 * q1; d2[1] = 0; d2[2] = 2 * q3;
+                    d3[0] = -2 * q0; d3[1] = -4 * q3; d3[2] = 2 * q2;
+                } else {
+                    d0[0] = 2 * q2; d0[1] = -2 * q1; d0[2] = 0;
+                    d1[0] = 2 * q3; d1[1] = -2 * q0; d1[2] = -4 * q1;
+                    d2[0] = 2 * q0; d2[1] = 2 * q3; d2[2] = -4 * q2;
+                    d3[0] = 2 * q1; d3[1] = 2 * q2; d3[2] = 0;
+                }
+                atomicAdd(r + REC_DROT + 0, dL_ddi * (w1 * d0[0] + w2 * d0[1] + w3 * d0[2]));
+                atomicAdd(r + REC_DROT + 1, dL_ddi * (w1 * d1[0] + w2 * d1[1] + w3 * d1[2]));
+                atomicAdd(r + REC_DROT + 2, dL_ddi * (w1 * d2[0] + w2 * d2[1] + w3 * d2[2]));
+                atomicAdd(r + REC_DROT + 3, dL_ddi * (w1 * d3[0] + w2 * d3[1] + w3 * d3[2]));
+            } else {
+                atomicAdd(r + REC_DMEAN + 0, dL_ddi * __ldg(vm + 2));
+                atomicAdd(r + REC_DMEAN + 1, dL_ddi * __ldg(vm + 6));
+                atomicAdd(r + REC_DMEAN + 2, dL_ddi * __ldg(vm + 10));
+            }
+        }
+    }
+}
+
+void launch_render_fwd(const ViewParams &vp, const GeomState &g, const BinState &b, const ImgState &img, const int32_t *counters,
+                       float *out_color, float *out_depth, int *out_hit_color, int *out_hit_depth, float *out_hcw,
+                       float *out_hdw, float *out_T, cudaStream_t s) {
+    const int T = vp.tiles_x * vp.tiles_y;
+    render_fwd_kernel<<<T, 256, 0, s>>>(vp, g, b, img, counters, out_color, out_depth, out_hit_color, out_hit_depth, out_hcw,
+                                        out_hdw, out_T);
+}
+
+void launch_render_bwd(const ViewParams &vp, const GeomState &g, const BinState &b, const ImgState &img, const int32_t *counters,
+                       const float *means, const float *scales, const float *rots, const float *final_T, const int *hit_image,
+                       const float *dL_dcolor, const float *dL_ddepth, float *rec, cudaStream_t s) {
+    const int T = vp.tiles_x * vp.tiles_y;
+    render_bwd_kernel<<<T, 256, 0, s>>>(vp, g, b, img, counters, means, scales, rots, final_T, hit_image, dL_dcolor, dL_ddepth, rec);
+}
+
+}  // namespace rtg

@@ -1,0 +1,321 @@
+"""Operator API of the reference rasterizer, backed by librtg_splat_b200.so.
+
+Mirrors `diff_gaussian_rasterization_depth/__init__.py` of the reference (RAST/...:29-372): same
+`GaussianRasterizationSettings` fields and defaults, same `GaussianRasterizer.forward` signature and
+exactly-one-of checks, same 8-tuple of outputs, same gradient tuple. What is different underneath:
+
+* the native side is a C ABI called through ctypes with raw pointers and the current stream;
+* no blocking read-backs: the instance count stays on the device. The binning buffer is sized from the
+  previous call; the scan kernel drops the counters into pinned host memory and the shim waits only for
+  that kernel (the rest of the forward keeps running) to detect the rare overflow, in which case the
+  forward is re-run with a larger buffer;
+* outputs and gradients are `torch.empty` -- the kernels write every element (the reference fills 9
+  tensors with `torch::full` / `zeros` first).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import RtgSplatView, check
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    opaque_threshold: float
+    normal_threshold: float
+    depth_threshold: float
+    prefiltered: bool
+    debug: bool
+    cx: float
+    cy: float
+    color_sigma: float = 3.0
+    T_threshold: float = 0.0001
+
+
+# ----------------------------------------------------------------------------- per-device state
+class _DeviceState:
+    """Capacity hint for the binning buffer, pinned counters, gradient scratch; one per CUDA device."""
+
+    def __init__(self, device):
+        self.device = device
+        self.r_hint = 1 << 16
+        self.scratch = None  # (P*16,) zeros, cleared by the backward kernel itself
+        self.ones_masks = {}
+        self.pinned = []  # free list of (pinned tensor, event)
+        self.sync_checks = True
+
+    def get_pinned(self):
+        if self.pinned:
+            return self.pinned.pop()
+        t = torch.zeros(_lib.RTG_CNT_WORDS, dtype=torch.int32).pin_memory()
+        return t, torch.cuda.Event()
+
+    def put_pinned(self, item):
+        self.pinned.append(item)
+
+    def get_scratch(self, P):
+        n = P * 16
+        if self.scratch is None or self.scratch.numel() < n:
+            self.scratch = torch.zeros(max(n, 1024), dtype=torch.float32, device=self.device)
+        return self.scratch
+
+    def ones_mask(self, th, tw):
+        key = (th, tw)
+        if key not in self.ones_masks:
+            self.ones_masks[key] = torch.ones((th, tw), dtype=torch.int32, device=self.device)
+        return self.ones_masks[key]
+
+
+_STATES = {}
+
+
+def _state(device) -> _DeviceState:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _STATES:
+        _STATES[idx] = _DeviceState(torch.device("cuda", idx))
+    return _STATES[idx]
+
+
+def set_async_capacity_checks(enabled: bool, device=None) -> None:
+    """enabled=False: never wait for the scan kernel; an overflow is then only detected at the next call
+    (the frame that overflowed renders as empty). Default True."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _state(dev).sync_checks = bool(enabled)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _opt(t):
+    """Empty tensor encodes 'not provided' (reference: torch.Tensor([]) -> nullptr)."""
+    return None if (t is None or t.numel() == 0) else t
+
+
+def _f32_cuda(t, name, device):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise TypeError(f"{name} must be a CUDA float32 tensor (got {t.dtype} on {t.device})")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    return t.contiguous()
+
+
+def _make_view(rs: GaussianRasterizationSettings, device) -> tuple[RtgSplatView, tuple]:
+    keep = tuple(_f32_cuda(x, n, device) for x, n in ((rs.viewmatrix, "viewmatrix"), (rs.projmatrix, "projmatrix"),
+                                                      (rs.campos, "campos"), (rs.bg, "bg")))
+    v = RtgSplatView()
+    v.image_height, v.image_width = int(rs.image_height), int(rs.image_width)
+    v.tanfovx, v.tanfovy = float(rs.tanfovx), float(rs.tanfovy)
+    v.cx, v.cy = float(rs.cx), float(rs.cy)
+    v.scale_modifier, v.color_sigma = float(rs.scale_modifier), float(rs.color_sigma)
+    v.opaque_threshold, v.depth_threshold = float(rs.opaque_threshold), float(rs.depth_threshold)
+    v.normal_threshold, v.T_threshold = float(rs.normal_threshold), float(rs.T_threshold)
+    v.sh_degree, v.prefiltered = int(rs.sh_degree), int(bool(rs.prefiltered))
+    v.viewmatrix, v.projmatrix, v.campos, v.bg = (k.data_ptr() for k in keep)
+    return v, keep
+
+
+class _Saved:
+    """State kept between forward and backward (the reference keeps geomBuffer / binningBuffer / imgBuffer)."""
+    __slots__ = ("geom", "img", "bin", "r_cap", "counters", "view_keep")
+
+
+def _forward_native(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask):
+    L = _lib.lib()
+    device = means3D.device
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise ValueError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:67-70
+    st = _state(device)
+    P = means3D.size(0)
+    H, W = int(rs.image_height), int(rs.image_width)
+    th, tw = (H + 15) // 16, (W + 15) // 16
+    means3D = _f32_cuda(means3D, "means3D", device)
+    sh = _f32_cuda(_opt(sh), "shs", device)
+    colors_precomp = _f32_cuda(_opt(colors_precomp), "colors_precomp", device)
+    opacities = _f32_cuda(opacities, "opacities", device)
+    scales = _f32_cuda(_opt(scales), "scales", device)
+    rotations = _f32_cuda(_opt(rotations), "rotations", device)
+    cov3Ds_precomp = _f32_cuda(_opt(cov3Ds_precomp), "cov3D_precomp", device)
+    if tile_mask is None:
+        tile_mask = st.ones_mask(th, tw)
+    if not tile_mask.is_cuda or tile_mask.dtype != torch.int32:
+        raise TypeError("tile_mask must be a CUDA int32 tensor")
+    tile_mask = tile_mask.contiguous()
+    if tile_mask.numel() != th * tw:
+        raise ValueError(f"tile_mask must have {th}x{tw} entries")
+    M = sh.size(1) if sh is not None else 0
+    view, keep = _make_view(rs, device)
+    stream = torch.cuda.current_stream(device).cuda_stream  # fetched per call: autograd runs backward on its own thread
+
+    f32 = dict(dtype=torch.float32, device=device)
+    i32 = dict(dtype=torch.int32, device=device)
+    color = torch.empty((3, H, W), **f32)
+    depth = torch.empty((1, H, W), **f32)
+    hit_color = torch.empty((1, H, W), **i32)
+    hit_depth = torch.empty((1, H, W), **i32)
+    hit_cw = torch.empty((1, H, W), **f32)
+    hit_dw = torch.empty((1, H, W), **f32)
+    T_map = torch.empty((1, H, W), **f32)
+    radii = torch.empty((P,), **i32)
+
+    gb, ib, bb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    saved = _Saved()
+    saved.view_keep = keep
+    r_cap = int(st.r_hint)
+    while True:
+        check(L.rtg_splat_workspace_bytes(P, H, W, r_cap, C.byref(gb), C.byref(ib), C.byref(bb)), "rtg_splat_workspace_bytes")
+        saved.geom = torch.empty(gb.value, dtype=torch.uint8, device=device)
+        saved.img = torch.empty(ib.value, dtype=torch.uint8, device=device)
+        saved.bin = torch.empty(bb.value, dtype=torch.uint8, device=device)
+        saved.counters = torch.empty(_lib.RTG_CNT_WORDS, **i32)
+        saved.r_cap = r_cap
+        pinned, event = st.get_pinned()
+        check(L.rtg_splat_forward(
+            C.byref(view), P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
+            _ptr(cov3Ds_precomp), _ptr(tile_mask), _ptr(saved.geom), _ptr(saved.img), _ptr(saved.bin), r_cap,
+            _ptr(color), _ptr(depth), _ptr(hit_color), _ptr(hit_depth), _ptr(hit_cw), _ptr(hit_dw), _ptr(T_map), _ptr(radii),
+            _ptr(saved.counters), C.c_void_p(pinned.data_ptr()), C.c_void_p(event.cuda_event), C.c_void_p(stream)),
+            "rtg_splat_forward")
+        if not st.sync_checks:
+            # deferred: use whatever the previous call reported (event may not have fired yet)
+            st.put_pinned((pinned, event))
+            break
+        event.synchronize()  # waits for the scan kernel only; scatter / sort / render are still running
+        num_rendered, overflow = int(pinned[0]), int(pinned[2])
+        st.put_pinned((pinned, event))
+        st.r_hint = max(st.r_hint, int(num_rendered * 1.25) + 4096)
+        if not overflow:
+            break
+        r_cap = int(st.r_hint)
+    return (color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii), saved, (means3D, sh, colors_precomp, scales, rotations,
+                                                                                    cov3Ds_precomp)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask, raster_settings):
+        outs, saved, inputs = _forward_native(raster_settings, means3D, sh, colors_precomp, opacities, scales, rotations,
+                                              cov3Ds_precomp, tile_mask)
+        color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii = outs
+        ctx.raster_settings = raster_settings
+        ctx.native = saved
+        ctx.provided = tuple(x is not None for x in inputs)
+        e = torch.empty(0, device=means3D.device)
+        ctx.save_for_backward(*[x if x is not None else e for x in inputs], radii, hit_depth, T_map)
+        ctx.mark_non_differentiable(hit_color, hit_depth, radii)
+        return color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_depth, grad_hit_color, grad_hit_depth, grad_hit_color_weight,
+                 grad_hit_depth_weight, grad_T_map, _):
+        L = _lib.lib()
+        rs = ctx.raster_settings
+        saved = ctx.native
+        means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii, hit_depth, T_map = ctx.saved_tensors
+        has = ctx.provided
+        sh = sh if has[1] else None
+        colors_precomp = colors_precomp if has[2] else None
+        scales = scales if has[3] else None
+        rotations = rotations if has[4] else None
+        cov3Ds_precomp = cov3Ds_precomp if has[5] else None
+        device = means3D.device
+        P = means3D.size(0)
+        M = sh.size(1) if sh is not None else 0
+        H, W = int(rs.image_height), int(rs.image_width)
+        f32 = dict(dtype=torch.float32, device=device)
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, H, W), **f32)
+        if grad_out_depth is None:
+            grad_out_depth = torch.zeros((1, H, W), **f32)
+        grad_out_color = _f32_cuda(grad_out_color, "grad_out_color", device)
+        grad_out_depth = _f32_cuda(grad_out_depth, "grad_out_depth", device)
+        view, keep = _make_view(rs, device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        st = _state(device)
+
+        g_means = torch.empty((P, 3), **f32)
+        g_opac = torch.empty((P, 1), **f32)
+        g_sh = torch.empty((P, M, 3), **f32) if sh is not None else None
+        g_colors = torch.empty((P, 3), **f32) if colors_precomp is not None else None
+        g_scales = torch.empty((P, 3), **f32) if scales is not None else None
+        g_rot = torch.empty((P, 4), **f32) if rotations is not None else None
+        g_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp is not None else None
+        scratch = st.get_scratch(P)
+        if P > 0:
+            check(L.rtg_splat_backward(
+                C.byref(view), P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp),
+                _ptr(radii), _ptr(saved.geom), _ptr(saved.img), _ptr(saved.bin), saved.r_cap, _ptr(saved.counters),
+                _ptr(T_map), _ptr(hit_depth), _ptr(grad_out_color), _ptr(grad_out_depth), _ptr(scratch),
+                _ptr(g_means), _ptr(g_sh), _ptr(g_colors), _ptr(g_opac), _ptr(g_scales), _ptr(g_rot), _ptr(g_cov), None,
+                C.c_void_p(stream)), "rtg_splat_backward")
+        # same order as the forward's arguments (reference __init__.py:269-279)
+        return g_means, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, None, None
+
+
+def rasterize_gaussians(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask, raster_settings):
+    return _RasterizeGaussians.apply(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask,
+                                     raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            L = _lib.lib()
+            device = positions.device
+            pos = _f32_cuda(positions, "positions", device)
+            P = pos.size(0)
+            present = torch.empty((P,), dtype=torch.bool, device=device)
+            vm = _f32_cuda(rs.viewmatrix, "viewmatrix", device)
+            pm = _f32_cuda(rs.projmatrix, "projmatrix", device)
+            if P > 0:
+                check(L.rtg_splat_mark_visible(P, _ptr(pos), _ptr(vm), _ptr(pm), _ptr(present),
+                                               C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "rtg_splat_mark_visible")
+        return present
+
+    def forward(self, means3D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
+                tile_mask=None, normal_w=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+            (scales is not None or rotations is not None) and cov3D_precomp is not None
+        ):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+
+        empty = torch.Tensor([])
+        if shs is None:
+            shs = empty
+        if colors_precomp is None:
+            colors_precomp = empty
+        if scales is None:
+            scales = empty
+        if rotations is None:
+            rotations = empty
+        if cov3D_precomp is None:
+            cov3D_precomp = empty
+
+        return rasterize_gaussians(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, tile_mask,
+                                   raster_settings)

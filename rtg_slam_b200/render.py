@@ -1,0 +1,87 @@
+"""`Renderer.render` of the reference (SLAM/render.py:21-145) on top of the B200 rasterizer.
+
+Same constructor arguments (an `args` bag with the `renderer_*`, `*_sh_degree`, `color_sigma` keys of
+configs/base.yaml:30-31,65-68), same `render(viewpoint_camera, gaussian_data, tile_mask=None)` call and the
+same result dictionary. The per-pixel normal map is produced without the boolean-mask indexing of the
+reference (render.py:130-133), which forces a host synchronisation (`nonzero`)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+
+class Renderer:
+    def __init__(self, args):
+        self.raster_settings = None
+        self.rasterizer = None
+        self.bg_color = torch.tensor([0, 0, 0], dtype=torch.float32, device="cuda")
+        self.renderer_opaque_threshold = args.renderer_opaque_threshold
+        self.renderer_normal_threshold = np.cos(np.deg2rad(args.renderer_normal_threshold))
+        self.scaling_modifier = 1.0
+        self.renderer_depth_threshold = args.renderer_depth_threshold
+        self.max_sh_degree = args.max_sh_degree
+        self.color_sigma = args.color_sigma
+        if args.active_sh_degree < 0:
+            self.active_sh_degree = self.max_sh_degree
+        else:
+            self.active_sh_degree = args.active_sh_degree
+
+    def render(self, viewpoint_camera, gaussian_data, tile_mask=None):
+        tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
+        tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
+        self.raster_settings = GaussianRasterizationSettings(
+            image_height=int(viewpoint_camera.image_height),
+            image_width=int(viewpoint_camera.image_width),
+            tanfovx=tanfovx,
+            tanfovy=tanfovy,
+            bg=self.bg_color,
+            scale_modifier=self.scaling_modifier,
+            viewmatrix=viewpoint_camera.world_view_transform,
+            projmatrix=viewpoint_camera.full_proj_transform,
+            sh_degree=self.active_sh_degree,
+            campos=viewpoint_camera.camera_center,
+            opaque_threshold=self.renderer_opaque_threshold,
+            depth_threshold=self.renderer_depth_threshold,
+            normal_threshold=self.renderer_normal_threshold,
+            color_sigma=self.color_sigma,
+            prefiltered=False,
+            debug=False,
+            cx=viewpoint_camera.cx,
+            cy=viewpoint_camera.cy,
+            T_threshold=0.0001,
+        )
+        self.rasterizer = GaussianRasterizer(raster_settings=self.raster_settings)
+
+        normal = gaussian_data["normal"]
+        res = self.rasterizer(
+            means3D=gaussian_data["xyz"],
+            opacities=gaussian_data["opacity"],
+            shs=gaussian_data["shs"],
+            colors_precomp=None,
+            scales=gaussian_data["scales"],
+            rotations=gaussian_data["rotations"],
+            cov3D_precomp=None,
+            normal_w=normal,
+            tile_mask=tile_mask,  # None -> all tiles (render.py:101-108)
+        )
+        rendered_image, rendered_depth, color_index_map, depth_index_map, color_hit_weight, depth_hit_weight, T_map = res[:7]
+
+        # normal[depth_index_map] where the index is > -1, zeros elsewhere (render.py:130-133)
+        valid = depth_index_map[0] > -1
+        idx = depth_index_map[0].clamp_min(0).long()
+        render_normal = (normal[idx] * valid[..., None]).permute(2, 0, 1).contiguous()
+
+        return {
+            "render": rendered_image,
+            "depth": rendered_depth,
+            "normal": render_normal,
+            "color_index_map": color_index_map,
+            "depth_index_map": depth_index_map,
+            "color_hit_weight": color_hit_weight,
+            "depth_hit_weight": depth_hit_weight,
+            "T_map": T_map,
+        }

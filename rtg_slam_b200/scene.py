@@ -288,11 +288,15 @@ def upstream_grads(cam: Camera, seed: int = 5):
 # depth frames for the ICP path
 # --------------------------------------------------------------------------
 
+DEFAULT_SPHERES = (((0.3, 0.1, 2.0), 0.6), ((-0.9, -0.3, 2.4), 0.45), ((1.0, 0.5, 2.6), 0.4), ((-0.2, 0.7, 1.6), 0.25),
+                   ((0.8, -0.6, 1.8), 0.3))
+
+
 def raycast_room_depth(cam: Camera, box=(6.0, 3.0, 6.0), noise_sigma: float = 0.0, seed: int = 3,
-                       sphere=((0.3, 0.1, 2.0), 0.6)) -> np.ndarray:
-    """z-depth (H,W) float32 of the box room (plus one sphere, so that normals
-    vary) seen from `cam.c2w`; optional Gaussian noise; values outside
-    [0.3, 5] m set to 0 (`configs/base.yaml:38-39` min/max depth)."""
+                       spheres=DEFAULT_SPHERES) -> np.ndarray:
+    """z-depth (H,W) float32 of the box room (plus a few spheres, so that all six pose degrees of freedom are
+    constrained) seen from `cam.c2w`; optional Gaussian noise; values outside [0.3, 5] m set to 0
+    (`configs/base.yaml:38-39` min/max depth)."""
     H, W = cam.height, cam.width
     j, i = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     d_c = np.stack([(i - cam.cx) / cam.fx, (j - cam.cy) / cam.fy, np.ones_like(i, dtype=np.float64)], -1)
@@ -304,8 +308,8 @@ def raycast_room_depth(cam: Camera, box=(6.0, 3.0, 6.0), noise_sigma: float = 0.
         t2 = (-half - t) / d_w
     tfar = np.minimum(np.maximum(t1, t2).min(-1), 1e9)
     depth = tfar.copy()  # ray parameter == z-depth because d_c.z == 1
-    if sphere is not None:
-        c, rad = np.array(sphere[0]), sphere[1]
+    for c, rad in (spheres or ()):
+        c = np.array(c)
         oc = t - c
         a = (d_w * d_w).sum(-1)
         b = 2 * (d_w * oc).sum(-1)

@@ -1,0 +1,141 @@
+"""Shared test helpers: scene -> torch tensors, calls into the product path, the oracle and (when its
+extension has been built into oracle/_ref/) the reference's own CUDA rasterizer."""
+from __future__ import annotations
+
+import glob
+import importlib.util
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DEFAULT_SETTINGS = dict(scale_modifier=1.0, color_sigma=3.0, opaque_threshold=0.6, depth_threshold=1.0,
+                        normal_threshold=float(np.cos(np.deg2rad(60.0))), T_threshold=1e-4, sh_degree=3)
+
+
+def to_torch(g, device):
+    return {k: torch.from_numpy(v).to(device) for k, v in g.items()}
+
+
+def make_settings(cam, device, **over):
+    from rtg_slam_b200.rasterizer import GaussianRasterizationSettings
+    st = dict(DEFAULT_SETTINGS)
+    st.update(over)
+    return GaussianRasterizationSettings(
+        image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.tensor(st.get("bg", (0.0, 0.0, 0.0)), dtype=torch.float32, device=device),
+        scale_modifier=st["scale_modifier"],
+        viewmatrix=torch.from_numpy(cam.viewmatrix).to(device), projmatrix=torch.from_numpy(cam.projmatrix).to(device),
+        sh_degree=st["sh_degree"], campos=torch.from_numpy(cam.campos).to(device),
+        opaque_threshold=st["opaque_threshold"], normal_threshold=st["normal_threshold"], depth_threshold=st["depth_threshold"],
+        prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy, color_sigma=st["color_sigma"], T_threshold=st["T_threshold"])
+
+
+def run_ours(cam, g, device, tile_mask=None, grads=None, **over):
+    """Forward (and backward if `grads`=(dL_dcolor, dL_ddepth) numpy) through the public operator API."""
+    from rtg_slam_b200.rasterizer import GaussianRasterizer
+    rs = make_settings(cam, device, **over)
+    t = to_torch(g, device)
+    leaves = {k: t[k].clone().requires_grad_(grads is not None) for k in ("xyz", "shs", "opacity", "scales", "rotations")}
+    tm = None if tile_mask is None else torch.from_numpy(np.ascontiguousarray(tile_mask, dtype=np.int32)).to(device)
+    out = GaussianRasterizer(rs)(means3D=leaves["xyz"], opacities=leaves["opacity"], shs=leaves["shs"], scales=leaves["scales"],
+                                 rotations=leaves["rotations"], tile_mask=tm)
+    res = dict(zip(("color", "depth", "hit_color", "hit_depth", "hit_color_weight", "hit_depth_weight", "T_map", "radii"),
+                   [o.detach().cpu().numpy() for o in out]))
+    if grads is not None:
+        gc = torch.from_numpy(grads[0]).to(device)
+        gd = torch.from_numpy(grads[1]).to(device)
+        loss = (out[0] * gc).sum() + (out[1] * gd).sum()
+        loss.backward()
+        res["grads"] = dict(means3D=leaves["xyz"].grad.cpu().numpy(), shs=leaves["shs"].grad.cpu().numpy(),
+                            opacities=leaves["opacity"].grad.cpu().numpy(), scales=leaves["scales"].grad.cpu().numpy(),
+                            rotations=leaves["rotations"].grad.cpu().numpy())
+    return res
+
+
+# ---------------------------------------------------------------- reference CUDA (oracle/_ref)
+_REF = None
+
+
+def ref_cuda_module():
+    """The reference's own `_C_depth` extension, built unmodified by oracle/build_ref.py. None if absent."""
+    global _REF
+    if _REF is None:
+        so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "_C_depth*.so"))
+        if not so:
+            _REF = False
+        else:
+            spec = importlib.util.spec_from_file_location("_C_depth", so[0])
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _REF = mod
+    return _REF or None
+
+
+def run_ref_cuda(cam, g, device, tile_mask=None, grads=None, **over):
+    """Calls rasterize_gaussians / rasterize_gaussians_backward of the reference exactly as its python shim does
+    (RAST/diff_gaussian_rasterization_depth/__init__.py:69-97,200-232)."""
+    mod = ref_cuda_module()
+    assert mod is not None
+    st = dict(DEFAULT_SETTINGS)
+    st.update(over)
+    t = to_torch(g, device)
+    H, W = cam.height, cam.width
+    th, tw = (H + 15) // 16, (W + 15) // 16
+    tm = torch.ones((th, tw), dtype=torch.int32, device=device) if tile_mask is None else \
+        torch.from_numpy(np.ascontiguousarray(tile_mask, dtype=np.int32)).to(device)
+    bg = torch.tensor(st.get("bg", (0.0, 0.0, 0.0)), dtype=torch.float32, device=device)
+    vm = torch.from_numpy(cam.viewmatrix).to(device)
+    pm = torch.from_numpy(cam.projmatrix).to(device)
+    cp = torch.from_numpy(cam.campos).to(device)
+    e = torch.Tensor([])
+    args = (bg, t["xyz"], e, t["opacity"], t["scales"], t["rotations"], st["scale_modifier"], e, vm, pm, tm, cam.tanfovx, cam.tanfovy,
+            H, W, cam.cx, cam.cy, t["shs"], st["sh_degree"], st["color_sigma"], cp, st["opaque_threshold"], st["depth_threshold"],
+            st["normal_threshold"], st["T_threshold"], False, False)
+    (num_rendered, num_tile, color, depth, hit_color, hit_depth, hcw, hdw, T_map, radii, geomB, binB, imgB, tile_indices) = \
+        mod.rasterize_gaussians(*args)
+    res = dict(color=color, depth=depth, hit_color=hit_color, hit_depth=hit_depth, hit_color_weight=hcw, hit_depth_weight=hdw,
+               T_map=T_map, radii=radii)
+    res = {k: v.cpu().numpy() for k, v in res.items()}
+    res["num_rendered"], res["num_tile"] = num_rendered, num_tile
+    if grads is not None:
+        gc = torch.from_numpy(grads[0]).to(device)
+        gd = torch.from_numpy(grads[1]).to(device)
+        bargs = (tile_indices, num_tile, bg, t["xyz"], radii, e, t["scales"], t["rotations"], st["scale_modifier"], e, vm, pm,
+                 cam.tanfovx, cam.tanfovy, cam.cx, cam.cy, st["depth_threshold"], st["normal_threshold"], gc, gd, t["shs"],
+                 st["sh_degree"], cp, geomB, num_rendered, binB, imgB, hit_depth, False)
+        (g2d, gcol, gop, gm3, gcov, gsh, gsc, grot) = mod.rasterize_gaussians_backward(*bargs)
+        res["grads"] = dict(means3D=gm3.cpu().numpy(), shs=gsh.cpu().numpy(), opacities=gop.cpu().numpy(), scales=gsc.cpu().numpy(),
+                            rotations=grot.cpu().numpy(), means2D=g2d.cpu().numpy(), colors=gcol.cpu().numpy(),
+                            cov3D=gcov.cpu().numpy())
+    return res
+
+
+# ---------------------------------------------------------------- comparison
+def rel_err(a, b):
+    """max|a-b| / (max|b| + 1e-12): the per-tensor gradient metric of SURVEY.md section 8(c)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12)) if a.size else 0.0
+
+
+def compare_outputs(a, b, tie=None, tol=1e-4, max_bad_frac=2e-4, label=""):
+    """Float maps: L_inf < tol on all pixels outside `tie` and on all but `max_bad_frac` of the pixels overall.
+    Index maps: exact outside `tie`, same outlier allowance. Returns a dict of statistics; raises AssertionError."""
+    H, W = a["color"].shape[-2:]
+    ok = np.ones((H, W), bool) if tie is None else ~tie.astype(bool)
+    idx_equal = (a["hit_color"][0] == b["hit_color"][0]) & (a["hit_depth"][0] == b["hit_depth"][0])
+    stats = {}
+    bad = ~idx_equal
+    for k in ("color", "depth", "hit_color_weight", "hit_depth_weight", "T_map"):
+        d = np.abs(a[k].astype(np.float64) - b[k].astype(np.float64)).max(axis=0)
+        stats[k] = float(d[ok & idx_equal].max()) if (ok & idx_equal).any() else 0.0
+        bad |= d >= tol
+    stats["bad_pixels"] = int((bad & ok).sum())
+    stats["tie_pixels"] = int((~ok).sum())
+    stats["radii_mismatch"] = int((a["radii"] != b["radii"]).sum())
+    frac = stats["bad_pixels"] / float(H * W)
+    assert frac <= max_bad_frac, f"{label}: {stats['bad_pixels']} pixels differ beyond tol ({frac:.2e} of the image): {stats}"
+    return stats
