@@ -1,0 +1,64 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/rtg_splat_b200.h declares; argument
+validation that happens before any CUDA call behaves as documented. No compute calls here."""
+import ctypes as C
+import os
+
+import pytest
+
+from rtg_slam_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_present_and_loads():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    L = _lib.lib()
+    assert L.rtg_version() >= 100
+
+
+def test_exports_every_header_symbol():
+    L = _lib.lib()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/rtg_splat_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
+
+
+def test_view_struct_layout_matches_header():
+    # 14 4-byte scalars then 4 pointers
+    assert C.sizeof(_lib.RtgSplatView) == 14 * 4 + 4 * 8
+    assert _lib.RtgSplatView.viewmatrix.offset == 56
+    assert C.sizeof(_lib.RtgAdamGroup) == 48
+
+
+def test_workspace_bytes_is_host_only_and_monotone():
+    L = _lib.lib()
+    g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert L.rtg_splat_workspace_bytes(1000, 480, 640, 10000, C.byref(g), C.byref(i), C.byref(b)) == 0
+    g2, i2, b2 = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert L.rtg_splat_workspace_bytes(2000, 480, 640, 20000, C.byref(g2), C.byref(i2), C.byref(b2)) == 0
+    assert g2.value > g.value and b2.value > b.value and i2.value == i.value
+    assert g.value >= 1000 * 76 and i.value >= 480 * 640 * 4 and b.value >= 10000 * 12
+    assert L.rtg_splat_workspace_bytes(-1, 480, 640, 0, None, None, None) == -1
+    assert b"bad sizes" in L.rtg_last_error()
+
+
+def test_forward_rejects_null_view_before_touching_cuda():
+    L = _lib.lib()
+    rc = L.rtg_splat_forward(None, 0, 0, *([None] * 8), None, None, None, 0, *([None] * 8), None, None, None, None)
+    assert rc == -1 and b"view is NULL" in L.rtg_last_error()
+
+
+def test_adam_rejects_bad_groups():
+    L = _lib.lib()
+    assert L.rtg_adam_step(None, 0, 0.9, 0.999, 1e-15, 1, None) == -1
+    arr = (_lib.RtgAdamGroup * 1)()
+    assert L.rtg_adam_step(arr, 1, 0.9, 0.999, 1e-15, 0, None) == -1  # step must be >= 1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.RtgError, match="no CPU or PyTorch fallback"):
+        _lib.lib()

@@ -1,0 +1,135 @@
+"""GPU parity tests of the ICP kernels and the fused Adam step, through the reference-facing Python classes."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import icp_oracle as io
+from rtg_slam_b200 import scene
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def tracker_args(**over):
+    a = dict(icp_downscales=[0.25, 0.5, 1.0], icp_warmup_frames=0, icp_use_model_depth=False, icp_downscale_iters=[5, 5, 5],
+             icp_distance_threshold=0.1, icp_normal_threshold=20, icp_damping=1e-4, verbose=False,
+             icp_sample_distance_threshold=0.01, icp_sample_normal_threshold=0.01, icp_fail_threshold=0.02)
+    a.update(over)
+    return types.SimpleNamespace(**a)
+
+
+@pytest.mark.parametrize("name", ["icp_small", "icp_ragged"])
+def test_pyramids_and_levels_match_reference_golden(cuda_device, name):
+    from rtg_slam_b200 import icp as ricp
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    K = tuple(float(k) for k in g["K"])
+    d0 = torch.from_numpy(g["depth0"]).to(cuda_device)
+    d1 = torch.from_numpy(g["depth1"]).to(cuda_device)
+    v0, n0 = ricp.build_pyramids(d0, K, 3)
+    v1, n1 = ricp.build_pyramids(d1, K, 3)
+    for i in range(3):
+        assert np.abs(v0[i].cpu().numpy() - g[f"v0_{i}"]).max() < 1e-6
+        assert np.abs(n0[i].cpu().numpy() - g[f"n0_{i}"]).max() < 1e-4
+        assert np.abs(n1[i].cpu().numpy() - g[f"n1_{i}"]).max() < 1e-4
+    pose = torch.eye(4, device=cuda_device)
+    for lvl, s in enumerate((0.25, 0.5, 1.0)):
+        tr = ricp.ICP(5, damping=1e-4, distance_threshold=0.1, normal_threshold=20)
+        Kl = tuple(float(np.float32(k) * np.float32(s)) for k in K)
+        pose, vr = tr.icp(pose, v1[lvl], v0[lvl], n1[lvl], n0[lvl], Kl)
+        assert np.linalg.norm(pose.cpu().numpy() - g["poses"][lvl]) < 1e-4, lvl
+        assert abs(float(vr) - g["valid_ratios"][lvl]) < 1e-3
+
+
+@pytest.mark.parametrize("camname", ["tum", "replica"])
+def test_tracker_matches_oracle_at_dataset_resolution(cuda_device, camname):
+    from rtg_slam_b200 import icp as ricp
+    cam0 = scene.make_camera(camname)
+    cam1 = scene.make_camera(camname, c2w=scene.small_pose())
+    d0 = scene.raycast_room_depth(cam0, noise_sigma=0.002, seed=3)
+    d1 = scene.raycast_room_depth(cam1, noise_sigma=0.002, seed=4)
+    K = (cam0.fx, cam0.fy, cam0.cx, cam0.cy)
+    pose_ref, loss_ref, vr_ref, ok_ref = io.predict_pose(d0, d1, K)
+    trk = ricp.IcpTracker(tracker_args())
+    Kt = torch.from_numpy(cam0.K)
+    trk.update_curr_status(torch.from_numpy(d0).to(cuda_device), Kt)
+    trk.move_last_status()
+    trk.update_curr_status(torch.from_numpy(d1).to(cuda_device), Kt)
+    pose, ok = trk.predict_pose({"K": Kt, "frame_id": 1})
+    assert isinstance(pose, np.ndarray) and pose.shape == (4, 4)
+    assert np.linalg.norm(pose - pose_ref) < 1e-4
+    assert ok == ok_ref and abs(trk.last_p2ploss - loss_ref) < 1e-5 + 1e-3 * loss_ref
+    # ground truth: pose maps current-frame points into the previous frame == c2w of the current camera
+    assert np.linalg.norm(pose - scene.small_pose()) < 5e-3
+
+
+def test_fill_model_depth(cuda_device):
+    from rtg_slam_b200 import icp as ricp
+    g = np.load(os.path.join(GOLD, "icp_small.npz"))
+    K = tuple(g["K"])
+    v0, n0 = io.build_pyramids(g["depth0"], K)
+    trk = ricp.IcpTracker(tracker_args())
+    rd = torch.from_numpy(g["fill_render_depth"].copy()).to(cuda_device)[..., None].contiguous()
+    trk.update_last_status(None, rd, torch.from_numpy(g["depth0"]).to(cuda_device)[..., None],
+                           torch.from_numpy(g["fill_render_normal"]).to(cuda_device), torch.from_numpy(n0[-1]).to(cuda_device))
+    assert (rd[..., 0].cpu().numpy() != g["fill_out"]).mean() < 1e-3
+    assert trk.last_model_depth is rd
+
+
+def test_fused_adam_matches_torch(cuda_device):
+    from rtg_slam_b200.optim import FusedAdam
+    dev = cuda_device
+    torch.manual_seed(0)
+    P = 5000
+    # the six groups of GaussianPointCloud.parametrize with the lrs of configs/base.yaml:82-86
+    shapes = [(P, 3), (P, 1, 3), (P, 15, 3), (P, 1), (P, 3), (P, 4)]
+    lrs = [1e-3, 5e-4, 5e-4 / 20.0, 0.0, 4e-3, 1e-3]
+    pa = [torch.randn(s, device=dev).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(pa, lrs)], lr=0.0, eps=1e-15)
+    ob = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(pb, lrs)], lr=0.0, eps=1e-15)
+    rng = np.random.default_rng(1)
+    for it in range(10):
+        for p, q in zip(pa, pb):
+            gr = torch.randn_like(p) * float(10 ** rng.uniform(-5, 0))
+            gr[::7] = 0  # exact zeros must stay harmless with eps=1e-15
+            p.grad, q.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+        oa.zero_grad(set_to_none=True); ob.zero_grad(set_to_none=True)
+    for p, q, lr in zip(pa, pb, lrs):
+        assert float((p - q).abs().max() / q.abs().max()) < 1e-5
+        if lr == 0.0:
+            assert torch.equal(p, q)  # opacity_lr is 0 in every shipped config: parameters must not move
+    sa, sb = oa.state[pa[2]], ob.state[pb[2]]
+    assert float((sa["exp_avg"] - sb["exp_avg"]).abs().max()) < 1e-6 * float(sb["exp_avg"].abs().max()) + 1e-12
+    # a parameter without a gradient is skipped, as in torch
+    pa[0].grad = None
+    before = pa[0].detach().clone()
+    pa[1].grad = torch.ones_like(pa[1])
+    oa.step()
+    assert torch.equal(before, pa[0])
+
+
+def test_renderer_api(cuda_device):
+    """Renderer.render returns the reference's dictionary; the normal map equals normal[depth_index_map]."""
+    from rtg_slam_b200.render import Renderer
+    import math
+    dev = cuda_device
+    cam = scene.make_camera("small")
+    g = scene.surfel_room(3000, seed=1)
+    args = types.SimpleNamespace(renderer_opaque_threshold=0.6, renderer_normal_threshold=60, renderer_depth_threshold=1.0,
+                                 max_sh_degree=3, color_sigma=3.0, active_sh_degree=3)
+    vc = types.SimpleNamespace(FoVx=2 * math.atan(cam.tanfovx), FoVy=2 * math.atan(cam.tanfovy), image_height=cam.height,
+                               image_width=cam.width, world_view_transform=torch.from_numpy(cam.viewmatrix).to(dev),
+                               full_proj_transform=torch.from_numpy(cam.projmatrix).to(dev),
+                               camera_center=torch.from_numpy(cam.campos).to(dev), cx=cam.cx, cy=cam.cy)
+    t = {k: torch.from_numpy(v).to(dev) for k, v in g.items()}
+    data = dict(xyz=t["xyz"], opacity=t["opacity"], scales=t["scales"], rotations=t["rotations"], shs=t["shs"], normal=t["normal"])
+    out = Renderer(args).render(vc, data)
+    assert set(out) == {"render", "depth", "normal", "color_index_map", "depth_index_map", "color_hit_weight", "depth_hit_weight", "T_map"}
+    idx = out["depth_index_map"][0]
+    ref = torch.zeros_like(out["render"])
+    ref[:, idx > -1] = t["normal"][idx[idx > -1].long()].permute(1, 0)  # the reference's own expression (render.py:130-133)
+    assert torch.equal(ref, out["normal"])

@@ -1,0 +1,211 @@
+"""GPU parity tests of the rasterizer (through the public operator API -> ctypes -> C ABI -> sm_100a kernels)
+against the CPU oracle, the committed golden outputs of the reference's CUDA code, and -- when oracle/_ref holds
+the reference extension -- the reference itself on the same device.
+
+Tolerances: float maps L_inf < 1e-4; index maps exact outside pixels whose deciding
+alpha / T is within 1e-4 (relative) of a threshold (flagged by the oracle); per-tensor gradient
+max|g-g_ref| / max|g_ref| < 1e-3 (and >= 10x the reference's own atomic-order jitter)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from golden.make_raster_golden import CASES, build_case
+from oracle.splat_oracle import OracleRender
+from rtg_slam_b200 import scene
+
+pytestmark = pytest.mark.gpu
+NAMES = ("color", "depth", "hit_color", "hit_depth", "hit_color_weight", "hit_depth_weight", "T_map", "radii")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GRADS = ("means3D", "shs", "opacities", "scales", "rotations")
+
+
+def oracle_outputs(o):
+    return dict(zip(NAMES, o.outputs()))
+
+
+def check_against_oracle(cam, g, dev, mask=None, label="", **over):
+    grads = scene.upstream_grads(cam, seed=5)
+    ours = helpers.run_ours(cam, g, dev, tile_mask=mask, grads=grads, **over)
+    o = OracleRender(cam, g, tile_mask=mask, precision="f32", tie_eps=1e-4, **over)
+    st = helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, tol=1e-4, label=label)
+    assert st["radii_mismatch"] == 0, st
+    og = o.backward(*grads)
+    for k in GRADS:
+        e = helpers.rel_err(ours["grads"][k], og[k])
+        assert e < 1e-3, f"{label}: d{k} rel err {e:.2e}"
+    return ours, o
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_matches_oracle_on_golden_scenes(cuda_device, name):
+    cam, g, mask, _ = build_case(name)
+    check_against_oracle(cam, g, cuda_device, mask=mask, label=name)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_matches_reference_cuda_golden(cuda_device, name):
+    path = os.path.join(GOLD, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture missing")
+    gold = np.load(path)
+    cam, g, mask, grads = build_case(name)
+    ours = helpers.run_ours(cam, g, cuda_device, tile_mask=mask, grads=grads)
+    o = OracleRender(cam, g, tile_mask=mask, precision="f32", tie_eps=1e-4)  # only for the tie mask
+    st = helpers.compare_outputs(ours, {k: gold[k] for k in NAMES}, tie=o.tie, tol=1e-4, label=name)
+    assert st["radii_mismatch"] == 0
+    for k in GRADS:
+        tol = max(1e-3, 10 * float(gold["jitter_" + k]))
+        assert helpers.rel_err(ours["grads"][k], gold["grad_" + k]) < tol, k
+
+
+@pytest.mark.parametrize("camname,P", [("tum", 10000), ("replica", 60000)])
+def test_matches_live_reference_cuda(cuda_device, camname, P):
+    if helpers.ref_cuda_module() is None:
+        pytest.skip("oracle/_ref not built")
+    cam = scene.make_camera(camname)
+    g = scene.surfel_room(P, seed=2024)
+    grads = scene.upstream_grads(cam, seed=5)
+    ours = helpers.run_ours(cam, g, cuda_device, grads=grads)
+    ref = helpers.run_ref_cuda(cam, g, cuda_device, grads=grads)
+    ref2 = helpers.run_ref_cuda(cam, g, cuda_device, grads=grads)
+    st = helpers.compare_outputs(ours, ref, tol=1e-4, max_bad_frac=5e-4, label=camname)
+    assert st["radii_mismatch"] == 0
+    for k in GRADS:
+        jitter = helpers.rel_err(ref2["grads"][k], ref["grads"][k])
+        assert helpers.rel_err(ours["grads"][k], ref["grads"][k]) < max(1e-3, 10 * jitter), (k, jitter)
+
+
+def test_sh_degrees_and_background(cuda_device):
+    cam = scene.make_camera("small")
+    g = scene.surfel_room(2000, seed=4)
+    for deg in (0, 1, 2):
+        check_against_oracle(cam, g, cuda_device, label=f"deg{deg}", sh_degree=deg)
+    check_against_oracle(cam, g, cuda_device, label="bg", bg=(0.2, 0.5, 0.9))
+
+
+def test_thresholds_variants(cuda_device):
+    cam = scene.make_camera("ragged")
+    g = scene.random_blobs(1500, seed=12)
+    check_against_oracle(cam, g, cuda_device, label="thr", opaque_threshold=0.3, depth_threshold=0.5,
+                         normal_threshold=float(np.cos(np.deg2rad(30.0))), color_sigma=2.0, T_threshold=1e-3)
+
+
+def test_edge_cases(cuda_device):
+    from rtg_slam_b200.rasterizer import GaussianRasterizer
+    dev = cuda_device
+    cam = scene.make_camera("tiny")
+    rs = helpers.make_settings(cam, dev)
+    # P == 0 (rasterize_points.cu short-circuits; outputs keep their initial values)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    out = GaussianRasterizer(rs)(means3D=z(0, 3), opacities=z(0, 1), shs=z(0, 16, 3), scales=z(0, 3), rotations=z(0, 4))
+    assert out[0].abs().max() == 0 and (out[6] == 1).all() and (out[2] == 0).all() and out[7].numel() == 0
+    # everything culled
+    g = scene.random_blobs(64, seed=3)
+    g["xyz"][:, 2] = -2.0
+    r = helpers.run_ours(cam, g, dev, grads=scene.upstream_grads(cam))
+    assert (r["radii"] == 0).all() and (r["T_map"] == 1).all() and (r["hit_depth"] == 0).all()
+    assert all(np.all(v == 0) for v in r["grads"].values())
+    # all tiles masked out
+    g = scene.random_blobs(200, seed=5)
+    th, tw = cam.tile_grid
+    r = helpers.run_ours(cam, g, dev, tile_mask=np.zeros((th, tw), np.int32), grads=scene.upstream_grads(cam))
+    assert (r["T_map"] == 1).all() and (r["color"] == 0).all()
+    assert all(np.all(v == 0) for v in r["grads"].values())
+    assert (r["radii"] > 0).any()  # radii are still reported for visible Gaussians, as in the reference
+
+
+def test_api_errors(cuda_device):
+    from rtg_slam_b200.rasterizer import GaussianRasterizer
+    dev = cuda_device
+    cam = scene.make_camera("tiny")
+    rs = helpers.make_settings(cam, dev)
+    t = helpers.to_torch(scene.random_blobs(10, seed=1), dev)
+    R = GaussianRasterizer(rs)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        R(means3D=t["xyz"], opacities=t["opacity"], scales=t["scales"], rotations=t["rotations"])
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        R(means3D=t["xyz"], opacities=t["opacity"], shs=t["shs"])
+    with pytest.raises(ValueError, match="means3D must have dimensions"):
+        R(means3D=t["xyz"].reshape(-1), opacities=t["opacity"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    with pytest.raises(TypeError, match="CUDA float32"):
+        R(means3D=t["xyz"].cpu(), opacities=t["opacity"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+
+
+def test_capacity_overflow_is_retried(cuda_device):
+    from rtg_slam_b200 import rasterizer
+    cam = scene.make_camera("small")
+    g = scene.surfel_room(3000, seed=1)
+    st = rasterizer._state(cuda_device)
+    st.r_hint = 16  # far too small: the first attempt must overflow and be re-run
+    ours = helpers.run_ours(cam, g, cuda_device)
+    o = OracleRender(cam, g, precision="f32", tie_eps=1e-4)
+    helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, label="overflow retry")
+    assert st.r_hint >= o.num_rendered
+
+
+def test_two_forwards_then_two_backwards(cuda_device):
+    """The saved state of each forward must stay valid if another render happens before its backward (the
+    reference allocates fresh buffers per call, rasterize_points.cu:89-96)."""
+    from rtg_slam_b200.rasterizer import GaussianRasterizer
+    dev = cuda_device
+    cams = [scene.make_camera("small"), scene.make_camera("small", c2w=scene.small_pose())]
+    g = scene.surfel_room(3000, seed=6)
+    t = helpers.to_torch(g, dev)
+    leaves = {k: t[k].clone().requires_grad_(True) for k in ("xyz", "shs", "opacity", "scales", "rotations")}
+    outs = []
+    for cam in cams:
+        rs = helpers.make_settings(cam, dev)
+        outs.append(GaussianRasterizer(rs)(means3D=leaves["xyz"], opacities=leaves["opacity"], shs=leaves["shs"],
+                                           scales=leaves["scales"], rotations=leaves["rotations"]))
+    gc, gd = scene.upstream_grads(cams[0], seed=5)
+    gct, gdt = torch.from_numpy(gc).to(dev), torch.from_numpy(gd).to(dev)
+    total = None
+    for i in (1, 0):  # backward in the opposite order
+        for v in leaves.values():
+            v.grad = None
+        ((outs[i][0] * gct).sum() + (outs[i][1] * gdt).sum()).backward()
+        o = OracleRender(cams[i], g, precision="f32")
+        og = o.backward(gc, gd)
+        assert helpers.rel_err(leaves["xyz"].grad.cpu().numpy(), og["means3D"]) < 1e-3
+        assert helpers.rel_err(leaves["shs"].grad.cpu().numpy(), og["shs"]) < 1e-3
+
+
+def test_forward_is_deterministic_and_mark_visible(cuda_device):
+    from rtg_slam_b200.rasterizer import GaussianRasterizer
+    cam = scene.make_camera("tum")
+    g = scene.surfel_room(20000, seed=8)
+    a = helpers.run_ours(cam, g, cuda_device)
+    b = helpers.run_ours(cam, g, cuda_device)
+    for k in NAMES:
+        assert np.array_equal(a[k], b[k]), k
+    rs = helpers.make_settings(cam, cuda_device)
+    vis = GaussianRasterizer(rs).markVisible(torch.from_numpy(g["xyz"]).to(cuda_device)).cpu().numpy()
+    assert vis.dtype == np.bool_ and np.all(vis[a["radii"] > 0])
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE.json's headline configuration (1 M Gaussians, 1200x680): size-independent properties."""
+    cam = scene.make_camera("replica")
+    g = scene.surfel_room(1_000_000, seed=2024)
+    mask = scene.random_tile_mask(cam, 0.5, seed=11)
+    grads = scene.upstream_grads(cam, seed=5)
+    r = helpers.run_ours(cam, g, cuda_device, tile_mask=mask, grads=grads)
+    T = r["T_map"][0]
+    assert (T > 0).all() and (T <= 1).all()
+    up = np.kron(mask, np.ones((16, 16), np.int32))[: cam.height, : cam.width].astype(bool)
+    assert (T[~up] == 1).all() and (r["color"][:, ~up] == 0).all() and (r["hit_depth"][0][~up] == 0).all()
+    hit = r["hit_depth"][0]
+    assert hit.max() < 1_000_000 and hit[up].min() >= -1
+    assert (r["radii"][hit[(hit >= 0) & up]] > 0).all()  # a hit refers to a visible Gaussian
+    assert (r["hit_depth_weight"][0][(hit >= 0) & up] > 0).all()
+    assert ((r["depth"][0] > 0) == ((hit >= 0) & up)).mean() > 0.9999
+    for k, v in r["grads"].items():
+        assert np.isfinite(v).all(), k
+        assert np.all(v[r["radii"] == 0] == 0), f"culled Gaussians must get exactly zero d{k}"
+    # linearity of the backward in the upstream gradient
+    r2 = helpers.run_ours(cam, g, cuda_device, tile_mask=mask, grads=(2 * grads[0], 2 * grads[1]))
+    for k in GRADS:
+        assert helpers.rel_err(r2["grads"][k], 2 * r["grads"][k]) < 1e-4, k
