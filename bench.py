@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: rasterizer fwd+bwd frames/s @ 1 M Gaussians, 1200x680 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for what every field means.
+* value      : frames/s with the Gaussian map, camera and upstream gradients resident in HBM (device events).
+* e2e        : frames/s through the public API (Renderer.render -> loss -> backward) with the RGB-D frame and the
+               camera matrices copied from pinned host memory and the loss read back every step.
+* roofline   : algorithmic bytes / measured duration of the dominant kernel.
+* cpu_baseline / --impl reference: the CPU oracle port of the reference algorithm on the host cores (the
+               reference ships no CPU render path; its rasterizer is CUDA-only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rasterizer fwd+bwd frames/sec @1M Gaussians 1200x680"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--camera", default="replica")
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference-CUDA / ICP / Adam side measurements")
+    return ap.parse_args()
+
+
+def workload_name(P, cam):
+    return f"surfel-room seed2024 P={P} {cam.width}x{cam.height} all tiles, sh_degree 3 (BASELINE configs[1] shape at the metric's 1M Gaussians)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm (CPU oracle port)
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.splat_oracle import OracleRender
+    from rtg_slam_b200 import scene
+    cam = scene.make_camera(args.camera)
+    g = scene.surfel_room(args.gaussians, seed=2024)
+    gc, gd = scene.upstream_grads(cam, seed=5)
+    cores = os.cpu_count() or 1
+    th, tw = cam.tile_grid
+
+    def one(mask):
+        t0 = time.perf_counter()
+        o = OracleRender(cam, g, tile_mask=mask, precision="f32", nthreads=cores)
+        o.backward(gc, gd, nthreads=cores)
+        o.close()
+        return time.perf_counter() - t0
+
+    # bounded sample: a fraction of the tiles if a full frame would blow the time budget
+    frac = 1.0
+    t_full = one(None)
+    budget = 150.0
+    n = args.steps + args.warmup
+    if t_full * n > budget:
+        frac = max(0.02, min(1.0, budget / (t_full * n)))
+    mask = None
+    if frac < 1.0:
+        rng = np.random.default_rng(0)
+        mask = (rng.uniform(size=(th, tw)) < frac).astype(np.int32)
+        frac = float(mask.mean())
+    for _ in range(max(0, args.warmup - 1)):
+        one(mask)
+    ts = [one(mask) for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    # per-tile work dominates: a frame costs t/frac (preprocess is amortised inside t and counted in full)
+    value = frac / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gaussians, cam)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{'full frame' if frac >= 1.0 else f'{frac:.3f} of the tiles of one frame (random tile mask), scaled'}; "
+                                   "oracle/splat_oracle.c (C restatement of the reference CUDA rasterizer, OpenMP over Gaussians and tiles); "
+                                   "the reference has no CPU render path"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from rtg_slam_b200 import _lib, scene
+    from rtg_slam_b200.rasterizer import GaussianRasterizer, GaussianRasterizationSettings
+    from rtg_slam_b200.render import Renderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices: the product path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    P = args.gaussians
+    # every rank renders its own frame of the same map: rank r looks from a slightly different pose
+    poses = [np.eye(4)] + [scene.small_pose((0.8 * r, -0.6 * r, 0.3 * r), (0.02 * r, -0.01 * r, 0.015 * r)) for r in range(1, 8)]
+    cam = scene.make_camera(args.camera, c2w=poses[rank % 8])
+    H, W = cam.height, cam.width
+
+    # the shared Gaussian map: generated on rank 0, broadcast over NCCL (north_star: "NCCL only to broadcast the shared map")
+    keys = ("xyz", "opacity", "scales", "rotations", "shs", "normal")
+    shapes = {"xyz": (P, 3), "opacity": (P, 1), "scales": (P, 3), "rotations": (P, 4), "shs": (P, 16, 3), "normal": (P, 3)}
+    if rank == 0:
+        g = scene.surfel_room(P, seed=2024)
+        t = {k: torch.from_numpy(g[k]).to(dev) for k in keys}
+    else:
+        t = {k: torch.empty(shapes[k], dtype=torch.float32, device=dev) for k in keys}
+    if world > 1:
+        for k in keys:
+            dist.broadcast(t[k], src=0)
+    leaves = {k: t[k].clone().requires_grad_(True) for k in ("xyz", "shs", "opacity", "scales", "rotations")}
+
+    def settings():
+        return GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3, device=dev), scale_modifier=1.0,
+            viewmatrix=torch.from_numpy(cam.viewmatrix).to(dev), projmatrix=torch.from_numpy(cam.projmatrix).to(dev), sh_degree=3,
+            campos=torch.from_numpy(cam.campos).to(dev), opaque_threshold=0.6, normal_threshold=float(np.cos(np.deg2rad(60.0))),
+            depth_threshold=1.0, prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy, color_sigma=3.0, T_threshold=1e-4)
+
+    rast = GaussianRasterizer(settings())
+    gc_np, gd_np = scene.upstream_grads(cam, seed=5)
+    gc, gd = torch.from_numpy(gc_np).to(dev), torch.from_numpy(gd_np).to(dev)
+
+    def step():
+        for v in leaves.values():
+            v.grad = None
+        out = rast(means3D=leaves["xyz"], opacities=leaves["opacity"], shs=leaves["shs"], scales=leaves["scales"],
+                   rotations=leaves["rotations"])
+        torch.autograd.backward([out[0], out[1]], [gc, gd])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    torch.cuda.synchronize()
+    counters = rast_counters(dev)
+    vis = int((out[7] > 0).sum())
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    _lib.profile_enable(False)
+    prof = _lib.profile_read(reset=True)
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    tm = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_step = float(tm.item()) / args.steps
+    value = world * 1e3 / ms_step  # every rank processed one frame per step
+
+    # ------------------------------------------------------------------ end to end through the public API
+    rargs = types.SimpleNamespace(renderer_opaque_threshold=0.6, renderer_normal_threshold=60, renderer_depth_threshold=1.0,
+                                  max_sh_degree=3, color_sigma=3.0, active_sh_degree=3)
+    renderer = Renderer(rargs)
+    # "measured" RGB-D frame of this step lives in pinned host memory, like a frame coming from the camera driver
+    with torch.no_grad():
+        ref_out = rast(means3D=t["xyz"], opacities=t["opacity"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+        frame_host = torch.cat([ref_out[0], ref_out[1]], 0).add_(0.01).cpu().pin_memory()  # (4,H,W)
+    view_host = torch.from_numpy(np.stack([cam.viewmatrix, cam.projmatrix])).pin_memory()
+    campos_host = torch.from_numpy(cam.campos).pin_memory()
+    frame_dev = torch.empty_like(frame_host, device=dev)
+    view_dev = torch.empty((2, 4, 4), device=dev)
+    campos_dev = torch.empty(3, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+    vc = types.SimpleNamespace(FoVx=2 * math.atan(cam.tanfovx), FoVy=2 * math.atan(cam.tanfovy), image_height=H, image_width=W,
+                               world_view_transform=view_dev[0], full_proj_transform=view_dev[1], camera_center=campos_dev, cx=cam.cx, cy=cam.cy)
+    data = dict(xyz=leaves["xyz"], opacity=leaves["opacity"], scales=leaves["scales"], rotations=leaves["rotations"], shs=leaves["shs"],
+                normal=t["normal"])
+
+    def e2e_step():
+        for v in leaves.values():
+            v.grad = None
+        frame_dev.copy_(frame_host, non_blocking=True)
+        view_dev.copy_(view_host, non_blocking=True)
+        campos_dev.copy_(campos_host, non_blocking=True)
+        out = renderer.render(vc, data)
+        color_loss = (out["render"] - frame_dev[:3]).abs().mean()          # l1_loss, utils/loss_utils.py:27
+        valid = ((out["depth_index_map"] != -1) & (frame_dev[3:4] > 0)).float()
+        depth_loss = ((out["depth"] - frame_dev[3:4]).abs() * valid).sum() / valid.sum().clamp_min(1.0)
+        loss = 0.8 * color_loss + 1.0 * depth_loss                          # configs/base.yaml:76-77 weights
+        loss.backward()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)       # the loss.item() of mapper.py:459
+        return float(loss_host[0])
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    tm = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e_value = world * 1e3 / (float(tm.item()) / args.steps)
+    h2d = frame_host.numel() * 4 + view_host.numel() * 4 + campos_host.numel() * 4
+    d2h = 4 + _lib.RTG_CNT_WORDS * 4  # loss + the mapped counters written by the scan kernel
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    R = int(counters[0]); n_tiles = int(counters[1])
+    N_a = H * W  # all tiles active, image is tile-aligned except the last half row
+    A = {  # algorithmic bytes per launch, SURVEY.md section 8(d)
+        "preprocess_fwd": 236 * P + 52 * vis,
+        "tile_scan": 0, "scatter": 12 * R, "tile_sort": 12 * R,
+        "render_fwd": 40 * R + 72 * N_a,
+        "render_bwd": 40 * R + 52 * N_a + 64 * vis,
+        "preprocess_bwd": (236 + 64 + 8) * vis + 236 * P,
+    }
+    kern = {k: (ms / max(c, 1), c) for k, (ms, c) in prof.items() if c > 0}
+    dom = max((k for k in kern if k in A), key=lambda k: kern[k][0] * kern[k][1])
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+        peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    ach = A[dom] / (kern[dom][0] * 1e-3) / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes": A[dom], "ms_per_launch": kern[dom][0],
+                "per_kernel": {k: {"ms": kern[k][0], "launches": kern[k][1], "algorithmic_GBps": (A.get(k, 0) / (kern[k][0] * 1e-3) / 1e9) if kern[k][0] > 0 else None}
+                               for k in kern}}
+    launches = sum(c for _, c in prof.values())
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(P, cam), "parallelism": "one frame per GPU per step on a replicated map (NCCL broadcast at start; no data-path collective)" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: 236 MB of Gaussian parameters + 76 MB of splat records + 236 MB of gradients are streamed every step (L2 = 126 MB)",
+                   "visible_gaussians": vis, "num_rendered": R, "active_tiles": n_tiles, "mean_tile_list": R / max(n_tiles, 1)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["cpu_baseline"] = cpu_baseline(args, cam)
+        line["extras"] = extras(dev, cam, t, leaves, step)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def rast_counters(dev):
+    """num_rendered / active tiles of the last forward (pinned copy written by the scan kernel)."""
+    from rtg_slam_b200 import rasterizer
+    st = rasterizer._state(dev)
+    pinned, ev = st.pinned[-1]
+    return [int(x) for x in pinned[:4]]
+
+
+def cpu_baseline(args, cam):
+    """The reference algorithm on the host cores (oracle port), one bounded sample of the same workload."""
+    from oracle.splat_oracle import OracleRender
+    from rtg_slam_b200 import scene
+    cores = os.cpu_count() or 1
+    g = scene.surfel_room(args.gaussians, seed=2024)
+    gc, gd = scene.upstream_grads(cam, seed=5)
+    th, tw = cam.tile_grid
+    rng = np.random.default_rng(0)
+    frac = 0.25
+    mask = (rng.uniform(size=(th, tw)) < frac).astype(np.int32)
+    t0 = time.perf_counter()
+    o = OracleRender(cam, g, tile_mask=mask, precision="f32", nthreads=cores)
+    o.backward(gc, gd, nthreads=cores)
+    o.close()
+    dt = time.perf_counter() - t0
+    return {"value": float(mask.mean()) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"one frame restricted to {mask.mean():.2f} of the tiles (random tile mask), fwd+bwd, scaled to a full frame; oracle/splat_oracle.c with OpenMP"}
+
+
+def extras(dev, cam, t, leaves, step):
+    """Side measurements reported next to the headline: reference CUDA rasterizer on this GPU, Adam step, ICP."""
+    import torch
+    from rtg_slam_b200 import scene
+    ex = {}
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import helpers
+        mod = helpers.ref_cuda_module()
+        if mod is not None:
+            g = {k: v.detach().cpu().numpy() for k, v in t.items()}
+            grads = scene.upstream_grads(cam, seed=5)
+            for _ in range(2):
+                helpers.run_ref_cuda(cam, g, dev, grads=grads)
+            ex["reference_cuda"] = time_ref_cuda(mod, cam, t, dev, grads)
+    except Exception as e:  # the comparator is optional
+        ex["reference_cuda"] = {"error": repr(e)}
+    # Adam over the six parameter groups (59 floats per Gaussian)
+    from rtg_slam_b200.optim import FusedAdam
+    P = t["xyz"].shape[0]
+    params = [torch.zeros(s, device=dev).requires_grad_(True) for s in ((P, 3), (P, 1, 3), (P, 15, 3), (P, 1), (P, 3), (P, 4))]
+    lrs = [1e-3, 5e-4, 2.5e-5, 0.0, 4e-3, 1e-3]
+    for name, cls in (("fused", FusedAdam), ("torch", torch.optim.Adam)):
+        opt = cls([{"params": [p], "lr": lr} for p, lr in zip(params, lrs)], lr=0.0, eps=1e-15)
+        for p in params:
+            p.grad = torch.randn_like(p)
+        for _ in range(3):
+            opt.step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            opt.step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        ex[f"adam_{name}_ms"] = ms
+        ex[f"adam_{name}_GBps"] = 1652 * P / (ms * 1e-3) / 1e9
+    # ICP: 3 levels x 5 iterations at this resolution
+    from rtg_slam_b200 import icp as ricp
+    cam1 = scene.make_camera("replica", c2w=scene.small_pose())
+    d0 = torch.from_numpy(scene.raycast_room_depth(scene.make_camera("replica"), noise_sigma=0.002, seed=3)).to(dev)
+    d1 = torch.from_numpy(scene.raycast_room_depth(cam1, noise_sigma=0.002, seed=4)).to(dev)
+    a_ = types.SimpleNamespace(icp_downscales=[0.25, 0.5, 1.0], icp_warmup_frames=0, icp_use_model_depth=False, icp_downscale_iters=[5, 5, 5],
+                               icp_distance_threshold=0.1, icp_normal_threshold=20, icp_damping=1e-4, verbose=False,
+                               icp_sample_distance_threshold=0.01, icp_sample_normal_threshold=0.01, icp_fail_threshold=0.02)
+    trk = ricp.IcpTracker(a_)
+    Kt = torch.from_numpy(cam.K)
+    trk.update_curr_status(d0, Kt); trk.move_last_status(); trk.update_curr_status(d1, Kt)
+    for _ in range(3):
+        trk.predict_pose({"K": Kt, "frame_id": 1})
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 20
+    for _ in range(n):
+        trk.predict_pose({"K": Kt, "frame_id": 1})
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    ex["icp_iters_per_s"] = 15 / dt
+    ex["icp_ms_per_predict_pose"] = dt * 1e3
+    ex["icp_note"] = "IcpTracker.predict_pose, 1200x680, levels 0.25/0.5/1.0 x 5 iterations, incl. the final pose read-back"
+    return ex
+
+
+def time_ref_cuda(mod, cam, t, dev, grads):
+    """The reference's own CUDA rasterizer (oracle/_ref) on the same tensors, fwd+bwd, CUDA events."""
+    import torch
+    H, W = cam.height, cam.width
+    th, tw = cam.tile_grid
+    tm = torch.ones((th, tw), dtype=torch.int32, device=dev)
+    bg = torch.zeros(3, device=dev)
+    vm = torch.from_numpy(cam.viewmatrix).to(dev); pm = torch.from_numpy(cam.projmatrix).to(dev); cp = torch.from_numpy(cam.campos).to(dev)
+    e = torch.Tensor([])
+    gc, gd = torch.from_numpy(grads[0]).to(dev), torch.from_numpy(grads[1]).to(dev)
+    nt = float(np.cos(np.deg2rad(60.0)))
+
+    def one():
+        r = mod.rasterize_gaussians(bg, t["xyz"], e, t["opacity"], t["scales"], t["rotations"], 1.0, e, vm, pm, tm, cam.tanfovx, cam.tanfovy,
+                                    H, W, cam.cx, cam.cy, t["shs"], 3, 3.0, cp, 0.6, 1.0, nt, 1e-4, False, False)
+        mod.rasterize_gaussians_backward(r[13], r[1], bg, t["xyz"], r[9], e, t["scales"], t["rotations"], 1.0, e, vm, pm, cam.tanfovx,
+                                         cam.tanfovy, cam.cx, cam.cy, 1.0, nt, gc, gd, t["shs"], 3, cp, r[10], r[0], r[11], r[12], r[5], False)
+        return r[0]
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    n = 10
+    for _ in range(n):
+        R = one()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    return {"ms_per_step": ms, "frames_per_s": 1e3 / ms, "num_rendered": int(R),
+            "note": "unmodified reference rasterizer (sm_100 build) called as its python shim does, same tensors, same GPU"}
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,15 @@ int rtg_icp_fill_model_depth(float *render_depth, const float *frame_depth, cons
                              const float *frame_normal, int32_t H, int32_t W, float distance_threshold,
                              float normal_threshold, void *stream);
 
+/* ---- measurement hook (no reference counterpart) ---------------------------------------------
+ * When enabled, every kernel launch of this library is bracketed by CUDA events on its launching stream.
+ * rtg_profile_read synchronises the device and returns, per kernel id, the summed duration (ms) and the number
+ * of launches since the last reset. bench.py uses it for the roofline line and the launch count. */
+int rtg_profile_enable(int32_t on);
+int rtg_profile_kernel_count(void);
+const char *rtg_profile_kernel_name(int32_t id);
+int rtg_profile_read(double *total_ms, int64_t *launches, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,10 @@ SIGNATURES = {
     "rtg_icp_solve_level": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _F, _F, _F, _F, _F, _I32, _VP, _VP, _VP, _VP]),
     "rtg_icp_point2plane_loss": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "rtg_icp_fill_model_depth": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _VP]),
+    "rtg_profile_enable": (C.c_int, [_I32]),
+    "rtg_profile_kernel_count": (C.c_int, []),
+    "rtg_profile_kernel_name": (C.c_char_p, [_I32]),
+    "rtg_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), _I32]),
 }
 
 _lib = None
@@ -88,3 +92,17 @@ def header_symbols():
     txt = open(hdr).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(rtg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().rtg_profile_enable(1 if on else 0), "rtg_profile_enable")
+
+
+def profile_read(reset: bool = True) -> dict:
+    """{kernel name: (total ms, launches)} since the last reset (synchronises the device)."""
+    L = lib()
+    n = L.rtg_profile_kernel_count()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(L.rtg_profile_read(ms, cnt, 1 if reset else 0), "rtg_profile_read")
+    return {L.rtg_profile_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}

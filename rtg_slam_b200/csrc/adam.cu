@@ -5,6 +5,7 @@
 // mapper.py:156,452): bias-corrected, no weight decay, no amsgrad. Pure streaming work:
 // 28 bytes per parameter (read p,g,m,v; write p,m,v), 128-bit accesses.
 #include "common.cuh"
+#include "prof.h"
 #include "../../include/rtg_splat_b200.h"
 
 namespace rtg {
@@ -79,6 +80,7 @@ int launch_adam(const RtgAdamGroup *groups, int n_groups, float beta1, float bet
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
     dim3 grid((unsigned)blocks, (unsigned)n_groups);
+    ProfScope ps(K_ADAM, s);
     adam_kernel<<<grid, 256, 0, s>>>(a);
     return 0;
 }

@@ -9,6 +9,7 @@
 // the order of the reference's stable sort, whose ties are broken by emission (= Gaussian) order.
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace rtg {
 
@@ -180,17 +181,20 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(BinState b, con
 
 // ---------------------------------------------------------------- launchers
 void launch_tile_scan(const BinState &b, int T, int64_t R_cap, int32_t *counters, int32_t *counters_host, cudaStream_t s) {
+    ProfScope ps(K_TILE_SCAN, s);
     tile_scan_kernel<<<1, 1024, 0, s>>>(b, T, (long long)R_cap, counters, counters_host);
 }
 
 void launch_scatter(const ViewParams &vp, int P, const GeomState &g, const int *radii, const int *tile_mask, const BinState &b,
                     int64_t R_cap, const int32_t *counters, cudaStream_t s) {
     if (P <= 0) return;
+    ProfScope ps(K_SCATTER, s);
     scatter_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, g, radii, tile_mask, b, (long long)R_cap, counters);
 }
 
 void launch_tile_sort(const BinState &b, int T, const int32_t *counters, cudaStream_t s) {
     if (T <= 0) return;
+    ProfScope ps(K_TILE_SORT, s);
     tile_sort_kernel<<<T, SORT_THREADS, 0, s>>>(b, counters);
 }
 

@@ -7,6 +7,9 @@
 #include "../../include/rtg_splat_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
+#include <vector>
+#include <mutex>
 
 namespace rtg {
 int launch_adam(const RtgAdamGroup *groups, int n_groups, float beta1, float beta2, float eps, int step, cudaStream_t s);
@@ -20,6 +23,40 @@ void launch_icp_p2p(const float *v_t0, const float *v_t1, const float *n_t0, int
                     void *ws, cudaStream_t s);
 void launch_icp_fill(float *render_depth, const float *frame_depth, const float *rn, const float *fn, int H, int W, float dthr,
                      float nthr, cudaStream_t s);
+}  // namespace rtg
+
+
+// ---------------------------------------------------------------- event profiler
+namespace rtg {
+struct ProfRec { int id; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::vector<ProfRec> g_prof_recs;
+static thread_local cudaEvent_t t_open[K_COUNT];
+
+static cudaEvent_t prof_get_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int id, cudaStream_t s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e = prof_get_event();
+    cudaEventRecord(e, s);
+    t_open[id] = e;
+}
+void prof_end(int id, cudaStream_t s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e = prof_get_event();
+    cudaEventRecord(e, s);
+    g_prof_recs.push_back({id, t_open[id], e});
+}
+static const char *kKernelNames[K_COUNT] = {"preprocess_fwd", "tile_scan", "scatter", "tile_sort", "render_fwd", "render_bwd",
+                                            "preprocess_bwd", "adam", "icp_build_level", "icp_iter", "icp_misc"};
 }  // namespace rtg
 
 static thread_local std::string g_err;
@@ -235,6 +272,33 @@ int rtg_icp_fill_model_depth(float *render_depth, const float *frame_depth, cons
     rtg::launch_icp_fill(render_depth, frame_depth, render_normal, frame_normal, H, W, distance_threshold, normal_threshold,
                          reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_icp_fill_model_depth");
+}
+
+int rtg_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(rtg::g_prof_mu);
+    rtg::g_prof_on = on != 0;
+    return RTG_OK;
+}
+
+int rtg_profile_kernel_count(void) { return rtg::K_COUNT; }
+
+const char *rtg_profile_kernel_name(int32_t id) { return (id >= 0 && id < rtg::K_COUNT) ? rtg::kKernelNames[id] : ""; }
+
+int rtg_profile_read(double *total_ms, int64_t *launches, int32_t reset) {
+    if (!total_ms || !launches) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_profile_read: NULL output");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_profile_read: ") + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lk(rtg::g_prof_mu);
+    for (int i = 0; i < rtg::K_COUNT; i++) { total_ms[i] = 0.0; launches[i] = 0; }
+    for (auto &r : rtg::g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { total_ms[r.id] += ms; launches[r.id] += 1; }
+    }
+    if (reset) {
+        for (auto &r : rtg::g_prof_recs) { rtg::g_prof_pool.push_back(r.a); rtg::g_prof_pool.push_back(r.b); }
+        rtg::g_prof_recs.clear();
+    }
+    return RTG_OK;
 }
 
 }  // extern "C"

@@ -7,6 +7,7 @@
 // terms (+ valid count) by a transposing warp butterfly and per-block double partials, and the last
 // block to finish solves the damped 6x6 system, applies exp_se3 and updates the pose in place.
 #include "common.cuh"
+#include "prof.h"
 #include "../../include/rtg_splat_b200.h"
 
 namespace rtg {
@@ -373,6 +374,7 @@ void launch_icp_build_level(const float *depth, int H, int W, int pool, float fx
                             float *normal, void *ws_, cudaStream_t s) {
     IcpWs *ws = reinterpret_cast<IcpWs *>(ws_);
     const int Hs = H / pool, Ws = W / pool;
+    ProfScope ps(K_ICP_BUILD, s);
     icp_ws_init_kernel<<<1, 1, 0, s>>>(ws);
     const int nb = (Hs * Ws + 255) / 256;
     icp_vertex_kernel<<<nb, 256, 0, s>>>(depth, H, W, pool, Hs, Ws, fx, fy, cx, cy, vertex, ws);
@@ -385,9 +387,11 @@ void launch_icp_solve_level(const float *v0, const float *n0, const float *v1, c
     IcpWs *ws = reinterpret_cast<IcpWs *>(ws_);
     icp_ws_init_kernel<<<1, 1, 0, s>>>(ws);
     const int nb = icp_blocks(H * W);
-    for (int it = 0; it < iters; it++)
+    for (int it = 0; it < iters; it++) {
+        ProfScope ps(K_ICP_ITER, s);
         icp_iter_kernel<<<nb, ICP_THREADS, 0, s>>>(v0, n0, v1, n1, H, W, fx, fy, cx, cy, dist_thr, cos_thr, damping, pose,
                                                    valid_ratio, ws);
+    }
 }
 
 void launch_icp_p2p(const float *v_t0, const float *v_t1, const float *n_t0, int H, int W, const float *pose, float *loss,

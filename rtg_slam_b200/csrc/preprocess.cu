@@ -8,6 +8,7 @@
 // once per (pixel, Gaussian) pair, and the backward consumes + clears a 64-byte gradient record.
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace rtg {
 
@@ -483,6 +484,7 @@ void launch_preprocess_fwd(const ViewParams &vp, int P, int M, const float *mean
                            const float *opac, const float *shs, const float *colors_precomp, const float *cov3D_precomp,
                            const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, cudaStream_t s) {
     if (P <= 0) return;
+    ProfScope ps(K_PREPROCESS_FWD, s);
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, opac, shs, colors_precomp, cov3D_precomp,
                                                           tile_mask, g, radii, tile_count);
 }
@@ -497,6 +499,7 @@ void launch_preprocess_bwd(const ViewParams &vp, int P, int M, const float *mean
                            float *dL_dmeans, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
                            float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s) {
     if (P <= 0) return;
+    ProfScope ps(K_PREPROCESS_BWD, s);
     preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, shs, cov3D_precomp, radii, g, rec,
                                                           dL_dmeans, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drot,
                                                           dL_dcov3D, dL_dmeans2D);

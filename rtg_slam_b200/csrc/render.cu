@@ -15,6 +15,7 @@
 //    and the pixel ray and are recomputed bit-identically in the backward.
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace rtg {
 
@@ -386,6 +387,7 @@ void launch_render_fwd(const ViewParams &vp, const GeomState &g, const BinState 
                        float *out_color, float *out_depth, int *out_hit_color, int *out_hit_depth, float *out_hcw,
                        float *out_hdw, float *out_T, cudaStream_t s) {
     const int T = vp.tiles_x * vp.tiles_y;
+    ProfScope ps(K_RENDER_FWD, s);
     render_fwd_kernel<<<T, 256, 0, s>>>(vp, g, b, img, counters, out_color, out_depth, out_hit_color, out_hit_depth, out_hcw,
                                         out_hdw, out_T);
 }
@@ -394,6 +396,7 @@ void launch_render_bwd(const ViewParams &vp, const GeomState &g, const BinState 
                        const float *means, const float *scales, const float *rots, const float *final_T, const int *hit_image,
                        const float *dL_dcolor, const float *dL_ddepth, float *rec, cudaStream_t s) {
     const int T = vp.tiles_x * vp.tiles_y;
+    ProfScope ps(K_RENDER_BWD, s);
     render_bwd_kernel<<<T, 256, 0, s>>>(vp, g, b, img, counters, means, scales, rots, final_T, hit_image, dL_dcolor, dL_ddepth, rec);
 }
 
