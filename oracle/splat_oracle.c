@@ -350,8 +350,27 @@ OracleState *oracle_forward(const OracleView *v, int P, int M, const real *means
             }
     }
     free(offs);
-    /* lexicographic sort of (key, idx) pairs: 16-byte records */
-    qsort(pk, (size_t)R, 2 * sizeof(uint64_t), oracle_cmp_pair);
+    /* Stable sort by (tile, depth) == lexicographic sort of (key, idx). Bucket by tile (counting sort on the
+     * high word), then sort every bucket independently (parallel over tiles). */
+    {
+        int64_t *tcount = (int64_t *)calloc((size_t)T + 1, sizeof(int64_t));
+        for (int64_t i = 0; i < R; i++) tcount[(pk[2 * i] >> 32) + 1]++;
+        for (int t2 = 0; t2 < T; t2++) tcount[t2 + 1] += tcount[t2];
+        uint64_t *pk2 = (uint64_t *)malloc(sizeof(uint64_t) * 2 * (size_t)(R + 1));
+        int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * ((size_t)T + 1));
+        memcpy(cur, tcount, sizeof(int64_t) * ((size_t)T + 1));
+        for (int64_t i = 0; i < R; i++) {
+            int64_t d = cur[pk[2 * i] >> 32]++;
+            pk2[2 * d] = pk[2 * i];
+            pk2[2 * d + 1] = pk[2 * i + 1];
+        }
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int t2 = 0; t2 < T; t2++)
+            if (tcount[t2 + 1] - tcount[t2] > 1)
+                qsort(pk2 + 2 * tcount[t2], (size_t)(tcount[t2 + 1] - tcount[t2]), 2 * sizeof(uint64_t), oracle_cmp_pair);
+        free(pk); free(cur); free(tcount);
+        pk = pk2;
+    }
     s->keys = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(R + 1));
     s->point_list = (int32_t *)malloc(sizeof(int32_t) * (size_t)(R + 1));
     for (int64_t i = 0; i < R; i++) { s->keys[i] = pk[2 * i]; s->point_list[i] = (int32_t)pk[2 * i + 1]; }
@@ -527,11 +546,12 @@ void oracle_backward(const OracleState *s, const real *dL_dpix, const real *dL_d
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
     nt = omp_get_max_threads();
+    if (nt > 16) nt = 16; /* each thread owns an 18*P-float accumulator set: cap the memory / reduction cost */
 #endif
     const size_t PP = (size_t)P;
     const size_t priv_stride = 18 * PP; /* color3 mean2D3 conic4 opac1 means3 rot4 */
     real *priv = nt > 1 ? (real *)calloc((size_t)(nt - 1) * priv_stride + 1, sizeof(real)) : NULL;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
     for (int tile = 0; tile < T; tile++) {
         int tid = 0;
 #ifdef _OPENMP

@@ -88,15 +88,20 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
     if (idx >= P) return;
     const int r = radii[idx];
     if (r <= 0) return;
+    const float4 s0 = g.splat[2 * (size_t)idx], s1 = g.splat[2 * (size_t)idx + 1];
     int x0, y0, x1, y1;
-    tile_rect(g.xy[idx], r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
-    const uint64_t key = ((uint64_t)__float_as_uint(g.depth[idx]) << 32) | (uint32_t)idx;
+    tile_rect(make_float2(s0.x, s0.y), r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
+    const uint64_t key = ((uint64_t)__float_as_uint(s0.w) << 32) | (uint32_t)idx;
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
             const int t = y * vp.tiles_x + x;
             if (__ldg(tile_mask + t)) {
-                const uint32_t pos = b.tile_offset[t] + atomicAdd(b.tile_fill + t, 1u);
-                b.keys[pos] = key;
+                const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
+                // same (bit-identical) decision as the histogram pass in preprocess_fwd_kernel
+                if (rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
+                const uint32_t slot = atomicAdd(b.tile_fill + t, 1u);
+                const uint32_t begin = b.tile_offset[t];
+                if (slot < b.tile_offset[t + 1] - begin) b.keys[begin + slot] = key;  // never write outside the bucket
             }
         }
 }

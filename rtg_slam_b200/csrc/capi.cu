@@ -161,11 +161,11 @@ int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const floa
     rtg::ImgState img = rtg::img_from(img_ws, (size_t)vp.H * vp.W);
     rtg::BinState b = rtg::bin_from(bin_ws, (size_t)T, (size_t)R_cap);
 
-    // tile_count and tile_fill are adjacent (bin_from): one clear
+    // tile_count, tile_fill and tile_touched are adjacent (bin_from): one clear
     cudaError_t e = cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)b.tile_offset - (char *)b.tile_count), s);
     if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward memset: ") + cudaGetErrorString(e));
     rtg::launch_preprocess_fwd(vp, P, M, means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp, tile_mask, g,
-                               radii, b.tile_count, s);
+                               radii, b.tile_count, b.tile_touched, s);
     rtg::launch_tile_scan(b, T, R_cap, counters, counters_host, s);
     if (scan_done_event) {
         e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(scan_done_event), s);

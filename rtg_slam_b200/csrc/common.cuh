@@ -22,24 +22,24 @@ struct ViewParams {
     const float *view, *proj, *campos, *bg;
 };
 
-// Per-Gaussian state written by the forward preprocess (SoA, 16-byte records so that every
-// gather in the render kernels is one LDG.128).
+// Per-Gaussian state written by the forward preprocess (16-byte records so that every gather in the render
+// kernels is one LDG.128; the two halves of `splat` share a 32-byte sector).
 struct GeomState {
-    float *depth;          // [P]   view-space z
-    float2 *xy;            // [P]   pixel-space centre
-    float4 *conic_opacity; // [P]   inverse 2-D covariance (a,b,c) + opacity
-    float4 *rgb_flags;     // [P]   SH colour (clamped at 0) + clamp bits (int in .w)
-    float4 *hit0;          // [P]   view-space normal (xyz) + scale_max*scale_modifier
-    float4 *hit1;          // [P]   view-space centre (xyz) + normal axis (int in .w)
+    float4 *splat;     // [2P]  [2i]   = pixel-space centre (x, y), q_cut, view-space depth
+                       //       [2i+1] = inverse 2-D covariance (a, b, c), opacity
+    float4 *rgb_flags; // [P]   SH colour (clamped at 0) + clamp bits (int in .w)
+    float4 *hit;       // [2P]  [2i]   = view-space normal (xyz), scale_max*scale_modifier
+                       //       [2i+1] = view-space centre (xyz), normal axis (int in .w)
 };
 
 struct BinState {
-    uint32_t *tile_count;  // [T]   instances per tile
-    uint32_t *tile_fill;   // [T]   scatter cursors
-    uint32_t *tile_offset; // [T+1] exclusive scan of tile_count
-    uint32_t *active;      // [T]   ascending ids of tiles with a non-empty list
-    uint64_t *keys;        // [R_cap] (depth bits << 32 | gaussian id), bucketed by tile
-    uint32_t *point_list;  // [R_cap] gaussian ids, per tile front-to-back
+    uint32_t *tile_count;   // [T]   instances per tile
+    uint32_t *tile_fill;    // [T]   scatter cursors
+    uint32_t *tile_touched; // [T]   1 if a Gaussian's rectangle covered the tile but the exact test culled it
+    uint32_t *tile_offset;  // [T+1] exclusive scan of tile_count
+    uint32_t *active;       // [T]   ascending ids of tiles with a non-empty list
+    uint64_t *keys;         // [R_cap] (depth bits << 32 | gaussian id), bucketed by tile
+    uint32_t *point_list;   // [R_cap] gaussian ids, per tile front-to-back
 };
 
 struct ImgState {
@@ -58,12 +58,9 @@ static inline T *carve(char *&p, size_t n) {
 static inline GeomState geom_from(void *ws, size_t P, size_t *bytes = nullptr) {
     char *p = reinterpret_cast<char *>(ws);
     GeomState g;
-    g.depth = carve<float>(p, P);
-    g.xy = carve<float2>(p, P);
-    g.conic_opacity = carve<float4>(p, P);
+    g.splat = carve<float4>(p, 2 * P);
     g.rgb_flags = carve<float4>(p, P);
-    g.hit0 = carve<float4>(p, P);
-    g.hit1 = carve<float4>(p, P);
+    g.hit = carve<float4>(p, 2 * P);
     if (bytes) *bytes = (size_t)(p - reinterpret_cast<char *>(ws));
     return g;
 }
@@ -71,9 +68,10 @@ static inline GeomState geom_from(void *ws, size_t P, size_t *bytes = nullptr) {
 static inline BinState bin_from(void *ws, size_t T, size_t R_cap, size_t *bytes = nullptr) {
     char *p = reinterpret_cast<char *>(ws);
     BinState b;
-    // tile_count and tile_fill are adjacent: one memset clears both
+    // tile_count, tile_fill and tile_touched are adjacent: one memset clears all three
     b.tile_count = carve<uint32_t>(p, T);
     b.tile_fill = carve<uint32_t>(p, T);
+    b.tile_touched = carve<uint32_t>(p, T);
     b.tile_offset = carve<uint32_t>(p, T + 1);
     b.active = carve<uint32_t>(p, T);
     b.keys = carve<uint64_t>(p, R_cap);
@@ -137,7 +135,62 @@ __device__ __forceinline__ void quat_to_R(const float4 q, float R[3][3]) {
     R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
 }
 
-__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+// Margin (in units of the exponent q = -power) added to ln(255*opacity): a (pixel, Gaussian) pair whose q
+// exceeds q_cut has alpha < (1/255)*exp(-Q_MARGIN), i.e. fails the reference's `alpha < 1/255` test with a
+// 1 % safety factor against fp32 rounding, so skipping it can never change an output.
+#define RTG_Q_MARGIN 0.01f
+
+// q_cut of a Gaussian: pairs with q > q_cut contribute nothing. Negative => contributes nowhere.
+__device__ __forceinline__ float q_cutoff(float opacity) {
+    const float t = 255.0f * opacity;
+    return (t < 0.999f) ? -1.0f : (logf(fmaxf(t, 0.999f)) + RTG_Q_MARGIN);
+}
+
+// True if q(d) = 0.5*(a dx^2 + c dy^2) + b dx dy > q_cut for EVERY point of the pixel rectangle
+// [x0,x1] x [y0,y1] (d = centre - pixel), i.e. the Gaussian cannot pass the alpha cut-off anywhere in it.
+// Exact minimisation of the convex quadratic over the rectangle (centre inside -> 0, else the minimum lies on
+// one of the four edges). Written with explicit round-to-nearest intrinsics so that every kernel that
+// evaluates it (histogram, scatter, per-warp masks) takes bit-identical decisions.
+__device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, float b, float c, float q_cut, float x0, float x1,
+                                                  float y0, float y1) {
+    if (q_cut < 0.f) return true;
+    if (!(a > 0.f) || !(c > 0.f)) return false;  // not a proper conic: keep the reference's behaviour
+    const float dxl = __fsub_rn(gx, x1), dxh = __fsub_rn(gx, x0), dyl = __fsub_rn(gy, y1), dyh = __fsub_rn(gy, y0);
+    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return false;
+    const float nb_c = __fdiv_rn(-b, c), nb_a = __fdiv_rn(-b, a);
+    float qmin;
+    {
+        const float dx = dxl, dy = fminf(dyh, fmaxf(dyl, __fmul_rn(nb_c, dx)));
+        qmin = __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy))));
+    }
+    {
+        const float dx = dxh, dy = fminf(dyh, fmaxf(dyl, __fmul_rn(nb_c, dx)));
+        qmin = fminf(qmin, __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy)))));
+    }
+    {
+        const float dy = dyl, dx = fminf(dxh, fmaxf(dxl, __fmul_rn(nb_a, dy)));
+        qmin = fminf(qmin, __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy)))));
+    }
+    {
+        const float dy = dyh, dx = fminf(dxh, fmaxf(dxl, __fmul_rn(nb_a, dy)));
+        qmin = fminf(qmin, __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy)))));
+    }
+    // the edge minimiser is exact up to rounding; shave a relative 1e-4 so that rounding can only keep, never cull
+    return __fmul_rn(qmin, 0.9999f) > q_cut;
+}
+
+// explicit shared-state-space accesses with a precomputed 32-bit base (keeps address arithmetic out of the loops)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 #endif
 
 }  // namespace rtg

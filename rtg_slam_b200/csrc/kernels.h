@@ -6,7 +6,8 @@ namespace rtg {
 
 void launch_preprocess_fwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
                            const float *opac, const float *shs, const float *colors_precomp, const float *cov3D_precomp,
-                           const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, cudaStream_t s);
+                           const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, uint32_t *tile_touched,
+                           cudaStream_t s);
 void launch_mark_visible(int P, const float *means, const float *view, const float *proj, uint8_t *present, cudaStream_t s);
 void launch_preprocess_bwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
                            const float *shs, const float *cov3D_precomp, const int *radii, const GeomState &g, float *rec,

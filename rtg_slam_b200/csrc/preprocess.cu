@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp
                                                              const float *__restrict__ shs, const float *__restrict__ colors_precomp,
                                                              const float *__restrict__ cov3D_precomp,
                                                              const int *__restrict__ tile_mask, GeomState g,
-                                                             int *__restrict__ radii, uint32_t *__restrict__ tile_count) {
+                                                             int *__restrict__ radii, uint32_t *__restrict__ tile_count,
+                                                             uint32_t *__restrict__ tile_touched) {
     __shared__ float s_m[40];
     if (threadIdx.x < 16) s_m[threadIdx.x] = vp.view[threadIdx.x];
     else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
@@ -216,19 +217,29 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp
         h1.w = __int_as_float(na);
     }
 
-    g.depth[idx] = pv.z;
+    const float opacity = __ldg(opac + idx);
+    const float q_cut = q_cutoff(opacity);
     radii[idx] = (int)my_radius;
-    g.xy[idx] = pix;
-    g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, __ldg(opac + idx));
+    g.splat[2 * (size_t)idx] = make_float4(pix.x, pix.y, q_cut, pv.z);
+    g.splat[2 * (size_t)idx + 1] = make_float4(conic.x, conic.y, conic.z, opacity);
     g.rgb_flags[idx] = make_float4(rgb.x, rgb.y, rgb.z, __int_as_float(flags));
-    g.hit0[idx] = h0;
-    g.hit1[idx] = h1;
+    g.hit[2 * (size_t)idx] = h0;
+    g.hit[2 * (size_t)idx + 1] = h1;
 
-    // tile histogram (only masked-in tiles, forward.cu:344-353)
+    // Tile histogram over the masked-in tiles of the reference's rectangle (forward.cu:344-353), minus the tiles
+    // in which no pixel can pass the alpha cut-off (exact test; such entries are skipped by every pixel of the
+    // reference's render loop, so dropping them changes no output). Tiles that lose all their entries this way
+    // are flagged: the reference still renders them (hit maps -1, colour = background).
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
             const int tt = y * vp.tiles_x + x;
-            if (__ldg(tile_mask + tt)) atomicAdd(tile_count + tt, 1u);
+            if (__ldg(tile_mask + tt)) {
+                const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
+                if (rect_below_cutoff(pix.x, pix.y, conic.x, conic.y, conic.z, q_cut, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1)))
+                    tile_touched[tt] = 1u;
+                else
+                    atomicAdd(tile_count + tt, 1u);
+            }
         }
 }
 
@@ -482,11 +493,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const ViewParams vp
 // ------------------------------------------------------------------ launchers
 void launch_preprocess_fwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
                            const float *opac, const float *shs, const float *colors_precomp, const float *cov3D_precomp,
-                           const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, cudaStream_t s) {
+                           const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, uint32_t *tile_touched,
+                           cudaStream_t s) {
     if (P <= 0) return;
     ProfScope ps(K_PREPROCESS_FWD, s);
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, opac, shs, colors_precomp, cov3D_precomp,
-                                                          tile_mask, g, radii, tile_count);
+                                                          tile_mask, g, radii, tile_count, tile_touched);
 }
 
 void launch_mark_visible(int P, const float *means, const float *view, const float *proj, uint8_t *present, cudaStream_t s) {

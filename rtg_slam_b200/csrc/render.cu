@@ -4,15 +4,21 @@
 // renderCUDA_flat (backward.cu:808-1066). What differs by design:
 //  * one CTA per tile over a device-resident tile table (no host-side tile compaction); CTAs of
 //    empty / masked-out tiles write the reference's initial values (rasterize_points.cu:79-87);
-//  * the plane hit is evaluated lazily, only for the first entry with alpha >= opaque_threshold,
-//    from a per-Gaussian view-space record (the reference recomputes quaternion->normal and two
-//    4x3 transforms from global memory for every blended pair, forward.cu:778-790);
-//  * the backward walks only the prefix of the tile list that some pixel of the CTA actually
-//    blended, reduces the 9 per-pair gradient terms across the warp with a transposing butterfly
-//    (16 shuffles instead of 45) and issues one multi-lane atomic per (warp, Gaussian) into a
-//    64-byte gradient record, instead of 9 atomics per (pixel, Gaussian) pair;
-//  * hit_normal_c / hit_point_c are not stored per pixel: they are functions of the hit Gaussian
-//    and the pixel ray and are recomputed bit-identically in the backward.
+//  * a warp owns an 8x4 pixel patch (the reference: a 16x2 strip). While a batch of 256 list entries is
+//    staged into shared memory, the staging thread also computes, once per entry, which of the 8 patches the
+//    Gaussian can reach above the alpha cut-off (exact convex minimisation, common.cuh). Each warp then walks
+//    only its own entries (ballot + find-first-set), so entries that every lane would skip are never visited;
+//  * per pair, the exponential is evaluated only if -power <= ln(255*opacity) + margin, i.e. only when the
+//    reference's `alpha < 1/255` test could pass;
+//  * the plane hit is evaluated lazily, only for the first entry with alpha >= opaque_threshold, from a
+//    per-Gaussian view-space record (the reference recomputes quaternion->normal and two 4x3 transforms from
+//    global memory for every blended pair, forward.cu:778-790);
+//  * the backward walks only the prefix of the tile list that some pixel of the CTA actually blended, reduces
+//    the 9 per-pair gradient terms across the warp with a transposing butterfly (16 shuffles instead of 45) and
+//    issues one 9-lane atomic per (warp, Gaussian) into a 64-byte gradient record, instead of 9 atomics per
+//    (pixel, Gaussian) pair;
+//  * hit_normal_c / hit_point_c are not stored per pixel: they are functions of the hit Gaussian and the pixel
+//    ray and are recomputed bit-identically in the backward.
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
@@ -20,18 +26,31 @@
 namespace rtg {
 
 #define BATCH 256
+#define FULL 0xffffffffu
 
+// warp w of the CTA owns the 8x4 patch (w & 1, w >> 1) of the 16x16 tile
 __device__ __forceinline__ void pixel_of(const ViewParams &vp, int tile, int &px, int &py, bool &inside) {
     const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
-    px = tx * RTG_TILE + (threadIdx.x & 15);
-    py = ty * RTG_TILE + (threadIdx.x >> 4);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    px = tx * RTG_TILE + (w & 1) * 8 + (lane & 7);
+    py = ty * RTG_TILE + (w >> 1) * 4 + (lane >> 3);
     inside = px < vp.W && py < vp.H;
 }
 
-// Plane / centre depth of the first opaque entry (forward.cu:778-809). Returns depth; outputs the
-// distance tests so that the backward can re-take the same branch.
+// bit k set <=> the Gaussian can pass the alpha cut-off somewhere in patch k of the tile at (tx0, ty0)
+__device__ __forceinline__ uint32_t patch_mask(const float4 s0, const float4 s1, float tx0, float ty0) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float x0 = tx0 + (float)((k & 1) * 8), y0 = ty0 + (float)((k >> 1) * 4);
+        if (!rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, x0, x0 + 7.f, y0, y0 + 3.f)) m |= (1u << k);
+    }
+    return m;
+}
+
+// Plane / centre depth of the first opaque entry (forward.cu:778-809).
 __device__ __forceinline__ float surfel_depth(const float4 h0, const float4 h1, const float3 ray, float center_depth,
-                                              float depth_thr, float normal_thr, bool &plane) {
+                                              float depth_thr, float normal_thr) {
     const float3 nc = make_float3(h0.x, h0.y, h0.z);
     const float3 pc = make_float3(h1.x, h1.y, h1.z);
     const float num = pc.x * nc.x + pc.y * nc.y + pc.z * nc.z;
@@ -41,7 +60,7 @@ __device__ __forceinline__ float surfel_depth(const float4 h0, const float4 h1, 
     const float hz = t * ray.z;
     const float angle_distance = fabsf(den);
     const float depth_distance = fabsf(hz - pc.z);
-    plane = (depth_distance <= h0.w * depth_thr) && (angle_distance >= normal_thr);
+    const bool plane = (depth_distance <= h0.w * depth_thr) && (angle_distance >= normal_thr);
     return plane ? hz : center_depth;
 }
 
@@ -50,10 +69,11 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                                                          float *__restrict__ out_depth, int *__restrict__ out_hit_color,
                                                          int *__restrict__ out_hit_depth, float *__restrict__ out_hcw,
                                                          float *__restrict__ out_hdw, float *__restrict__ out_T) {
-    __shared__ int s_id[BATCH];
-    __shared__ float2 s_xy[BATCH];
-    __shared__ float4 s_co[BATCH];
+    __shared__ float4 s_s0[BATCH];
+    __shared__ float4 s_s1[BATCH];
     __shared__ float4 s_rgb[BATCH];
+    __shared__ int s_id[BATCH];
+    __shared__ uint32_t s_mask[BATCH];
 
     const int tile = blockIdx.x;
     int px, py;
@@ -61,15 +81,22 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
     pixel_of(vp, tile, px, py, inside);
     const int pix_id = vp.W * py + px;
     const int N = vp.H * vp.W;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
     const bool overflow = counters[2] != 0;
     const uint32_t start = b.tile_offset[tile];
     const int n = overflow ? 0 : (int)(b.tile_offset[tile + 1] - start);
     if (n == 0) {
         if (inside) {
-            out_color[pix_id] = 0.f; out_color[N + pix_id] = 0.f; out_color[2 * N + pix_id] = 0.f;
+            // never-rendered tile: the wrapper's initial values (hit maps 0). A tile whose entries were all culled by
+            // the exact test is still "rendered" by the reference: hit maps -1, colour = background.
+            const bool touched = !overflow && b.tile_touched[tile] != 0u;
+            out_color[pix_id] = touched ? __ldg(vp.bg) : 0.f;
+            out_color[N + pix_id] = touched ? __ldg(vp.bg + 1) : 0.f;
+            out_color[2 * N + pix_id] = touched ? __ldg(vp.bg + 2) : 0.f;
             out_depth[pix_id] = 0.f;
-            out_hit_color[pix_id] = 0; out_hit_depth[pix_id] = 0;
+            out_hit_color[pix_id] = touched ? -1 : 0;
+            out_hit_depth[pix_id] = touched ? -1 : 0;
             out_hcw[pix_id] = 0.f; out_hdw[pix_id] = 0.f;
             out_T[pix_id] = 1.f;
             img.n_contrib[pix_id] = 0u;
@@ -79,10 +106,14 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
 
     const float2 pixf = make_float2((float)px, (float)py);
     const float3 ray = pixel_ray(px, py, vp.focal_x, vp.focal_y, vp.cx, vp.cy);
+    const float tx0 = (float)((tile % vp.tiles_x) * RTG_TILE), ty0 = (float)((tile / vp.tiles_x) * RTG_TILE);
+    const uint32_t a_s0 = smem_addr(s_s0), a_s1 = smem_addr(s_s1), a_rgb = smem_addr(s_rgb), a_id = smem_addr(s_id),
+                   a_mask = smem_addr(s_mask);
+    const float opaque_thr = vp.opaque_thr, T_thr = vp.T_thr;
     bool done = !inside;
 
     float T = 1.0f, end_T = 1.0f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
     float depth_ = 0.f;
     bool hit = false;
@@ -90,55 +121,68 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
     float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
 
     const int rounds = (n + BATCH - 1) / BATCH;
-    int toDo = n;
-    for (int i = 0; i < rounds; i++, toDo -= BATCH) {
+    for (int i = 0; i < rounds; i++) {
         if (__syncthreads_count(done) == BATCH) break;
         const int progress = i * BATCH + threadIdx.x;
         if (progress < n) {
             const int id = (int)b.point_list[start + progress];
+            const float4 s0 = __ldg(g.splat + 2 * (size_t)id), s1 = __ldg(g.splat + 2 * (size_t)id + 1);
             s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = g.xy[id];
-            s_co[threadIdx.x] = g.conic_opacity[id];
-            s_rgb[threadIdx.x] = g.rgb_flags[id];
+            s_s0[threadIdx.x] = s0;
+            s_s1[threadIdx.x] = s1;
+            s_rgb[threadIdx.x] = __ldg(g.rgb_flags + id);
+            s_mask[threadIdx.x] = patch_mask(s0, s1, tx0, ty0);
         }
         __syncthreads();
-        const int cnt = min(BATCH, toDo);
-        for (int j = 0; !done && j < cnt; j++) {
-            contributor++;
-            const float2 xy = s_xy[j];
-            const float dx = xy.x - pixf.x, dy = xy.y - pixf.y;
-            const float4 co = s_co[j];
-            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, co.w * expf(power));
-            if (alpha < 1.0f / 255.0f) continue;
-
-            if (!hit && alpha >= vp.opaque_thr) {
-                const int id = s_id[j];
-                bool plane;
-                depth_ = surfel_depth(g.hit0[id], g.hit1[id], ray, g.depth[id], vp.depth_thr, vp.normal_thr, plane);
-                hit_id = id;
-                hit_dw = alpha * T;
-                hit = true;
-            }
-            const float test_T = T * (1.f - alpha);
-            if (test_T < vp.T_thr && hit) {
-                done = true;
-                continue;
-            }
-            if (test_T >= vp.T_thr) {
-                const float cw = alpha * T;
-                const float4 c = s_rgb[j];
-                C0 += c.x * cw; C1 += c.y * cw; C2 += c.z * cw;
-                if (cw > cw_max) {
-                    cw_max = cw;
-                    hit_color_id = s_id[j];
-                    hit_cw = cw;
+        const int cnt = min(BATCH, n - i * BATCH);
+        if (__all_sync(FULL, done)) continue;  // warp-uniform
+        const int chunks = (cnt + 31) >> 5;
+        for (int c = 0; c < chunks; c++) {
+            const int e = (c << 5) + lane;
+            const uint32_t mm = (e < cnt) ? lds32(a_mask + e * 4) : 0u;
+            uint32_t bits = __ballot_sync(FULL, (mm >> w) & 1u);
+            while (bits) {
+                const int j = (c << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (!done) {
+                    const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
+                    const float dx = s0.x - pixf.x, dy = s0.y - pixf.y;
+                    const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
+                    // power > 0: skipped by the reference; power < -q_cut: alpha is certainly below 1/255
+                    if (power <= 0.0f && power >= -s0.z) {
+                        const float alpha = fminf(0.99f, s1.w * expf(power));
+                        if (alpha >= 1.0f / 255.0f) {
+                            if (!hit && alpha >= opaque_thr) {
+                                const int id = (int)lds32(a_id + j * 4);
+                                depth_ = surfel_depth(__ldg(g.hit + 2 * (size_t)id), __ldg(g.hit + 2 * (size_t)id + 1), ray, s0.w,
+                                                      vp.depth_thr, vp.normal_thr);
+                                hit_id = id;
+                                hit_dw = alpha * T;
+                                hit = true;
+                            }
+                            const float test_T = T * (1.f - alpha);
+                            if (test_T < T_thr) {
+                                // no colour is added any more; the pixel keeps scanning until it has an opaque hit
+                                if (hit) done = true;
+                                else T = test_T;
+                            } else {
+                                const float cw = alpha * T;
+                                const float4 col = lds128(a_rgb + j * 16);
+                                C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
+                                if (cw > cw_max) {
+                                    cw_max = cw;
+                                    hit_color_id = (int)lds32(a_id + j * 4);
+                                    hit_cw = cw;
+                                }
+                                last_contributor = (uint32_t)(i * BATCH + j + 1);
+                                end_T = test_T;
+                                T = test_T;
+                            }
+                        }
+                    }
                 }
-                last_contributor = contributor;
-                end_T = test_T;
+                if (__all_sync(FULL, done)) { bits = 0u; c = chunks; }
             }
-            T = test_T;
         }
     }
 
@@ -168,7 +212,7 @@ __device__ __forceinline__ void warp_transpose_reduce16(float v[16], const int l
         for (int i = 0; i < 8; i++) {
             const float send = hi ? v[i] : v[i + 8];
             const float keep = hi ? v[i + 8] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
         }
     }
     {
@@ -177,7 +221,7 @@ __device__ __forceinline__ void warp_transpose_reduce16(float v[16], const int l
         for (int i = 0; i < 4; i++) {
             const float send = hi ? v[i] : v[i + 4];
             const float keep = hi ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
         }
     }
     {
@@ -186,16 +230,16 @@ __device__ __forceinline__ void warp_transpose_reduce16(float v[16], const int l
         for (int i = 0; i < 2; i++) {
             const float send = hi ? v[i] : v[i + 2];
             const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            v[i] = keep + __shfl_xor_sync(FULL, send, 4);
         }
     }
     {
         const bool hi = lane & 2;
         const float send = hi ? v[0] : v[1];
         const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
     }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
 }
 
 __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b, const ImgState img,
@@ -204,10 +248,11 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
                                                          const float *__restrict__ final_T, const int *__restrict__ hit_image,
                                                          const float *__restrict__ dL_dcolor, const float *__restrict__ dL_ddepth,
                                                          float *__restrict__ rec) {
-    __shared__ int s_id[BATCH];
-    __shared__ float2 s_xy[BATCH];
-    __shared__ float4 s_co[BATCH];
+    __shared__ float4 s_s0[BATCH];
+    __shared__ float4 s_s1[BATCH];
     __shared__ float4 s_rgb[BATCH];
+    __shared__ int s_id[BATCH];
+    __shared__ uint32_t s_mask[BATCH];
     __shared__ uint32_t s_max[8];
 
     if (counters[2]) return;
@@ -220,8 +265,11 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
     pixel_of(vp, tile, px, py, inside);
     const int pix_id = vp.W * py + px;
     const int N = vp.H * vp.W;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float2 pixf = make_float2((float)px, (float)py);
+    const float tx0 = (float)((tile % vp.tiles_x) * RTG_TILE), ty0 = (float)((tile / vp.tiles_x) * RTG_TILE);
+    const uint32_t a_s0 = smem_addr(s_s0), a_s1 = smem_addr(s_s1), a_rgb = smem_addr(s_rgb), a_id = smem_addr(s_id),
+                   a_mask = smem_addr(s_mask);
 
     const float T_final = inside ? final_T[pix_id] : 0.f;
     float T = T_final;
@@ -236,12 +284,12 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
     // only the first `m` entries of the list were blended by some pixel of this tile
     uint32_t wmax = last_contributor;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max[wid] = wmax;
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, o));
+    if (lane == 0) s_max[w] = wmax;
     __syncthreads();
     uint32_t m = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) m = max(m, s_max[w]);
+    for (int k = 0; k < 8; k++) m = max(m, s_max[k]);
 
     float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
@@ -253,65 +301,74 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
         const int progress = i * BATCH + threadIdx.x;  // position from the back of the prefix
         if (progress < (int)m) {
             const int id = (int)b.point_list[start + (m - 1 - progress)];
+            const float4 s0 = __ldg(g.splat + 2 * (size_t)id), s1 = __ldg(g.splat + 2 * (size_t)id + 1);
             s_id[threadIdx.x] = id;
-            s_xy[threadIdx.x] = g.xy[id];
-            s_co[threadIdx.x] = g.conic_opacity[id];
-            s_rgb[threadIdx.x] = g.rgb_flags[id];
+            s_s0[threadIdx.x] = s0;
+            s_s1[threadIdx.x] = s1;
+            s_rgb[threadIdx.x] = __ldg(g.rgb_flags + id);
+            s_mask[threadIdx.x] = patch_mask(s0, s1, tx0, ty0);
         }
         __syncthreads();
         const int cnt = min(BATCH, (int)m - i * BATCH);
-        for (int j = 0; j < cnt; j++) {
-            const uint32_t pos = m - 1 - (uint32_t)(i * BATCH + j);  // 0-based list position == reference `contributor`
-            if (pos >= wmax) continue;                               // warp-uniform
-            float v[16];
+        const int chunks = (cnt + 31) >> 5;
+        for (int c = 0; c < chunks; c++) {
+            const int e = (c << 5) + lane;
+            // list position of staged entry e (== the reference's `contributor`); entries at or beyond the warp's
+            // deepest blended position are skipped by every lane
+            const uint32_t pos_e = m - 1 - (uint32_t)(i * BATCH + e);
+            const uint32_t mm = (e < cnt && pos_e < wmax) ? lds32(a_mask + e * 4) : 0u;
+            uint32_t bits = __ballot_sync(FULL, (mm >> w) & 1u);
+            while (bits) {
+                const int j = (c << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t pos = m - 1 - (uint32_t)(i * BATCH + j);
+                float v[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = 0.f;
-            bool active = pos < last_contributor;
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-            float4 co = s_co[j];
-            if (active) {
-                const float2 xy = s_xy[j];
-                dx = xy.x - pixf.x; dy = xy.y - pixf.y;
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                active = !(power > 0.0f);
+                for (int k = 0; k < 16; k++) v[k] = 0.f;
+                bool active = pos < last_contributor;
                 if (active) {
-                    G = expf(power);
-                    alpha = fminf(0.99f, co.w * G);
-                    active = !(alpha < 1.0f / 255.0f);
+                    const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
+                    const float dx = s0.x - pixf.x, dy = s0.y - pixf.y;
+                    const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
+                    active = (power <= 0.0f) && (power >= -s0.z);
+                    if (active) {
+                        const float G = expf(power);
+                        const float alpha = fminf(0.99f, s1.w * G);
+                        active = !(alpha < 1.0f / 255.0f);
+                        if (active) {
+                            T = T / (1.f - alpha);
+                            const float dch = alpha * T;
+                            const float4 col = lds128(a_rgb + j * 16);
+                            accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0; lc0 = col.x;
+                            accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1; lc1 = col.y;
+                            accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2; lc2 = col.z;
+                            float dL_dalpha = (col.x - accum0) * dLp0;
+                            dL_dalpha += (col.y - accum1) * dLp1;
+                            dL_dalpha += (col.z - accum2) * dLp2;
+                            v[REC_COLOR + 0] = dch * dLp0;
+                            v[REC_COLOR + 1] = dch * dLp1;
+                            v[REC_COLOR + 2] = dch * dLp2;
+                            dL_dalpha *= T;
+                            last_alpha = alpha;
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                            const float dL_dG = s1.w * dL_dalpha;
+                            const float gdx = G * dx, gdy = G * dy;
+                            const float dG_ddelx = -gdx * s1.x - gdy * s1.y;
+                            const float dG_ddely = -gdy * s1.z - gdx * s1.y;
+                            v[REC_MEAN2D + 0] = dL_dG * dG_ddelx * ddelx_dx;
+                            v[REC_MEAN2D + 1] = dL_dG * dG_ddely * ddely_dy;
+                            v[REC_CONIC + 0] = -0.5f * gdx * dx * dL_dG;
+                            v[REC_CONIC + 1] = -0.5f * gdx * dy * dL_dG;
+                            v[REC_CONIC + 2] = -0.5f * gdy * dy * dL_dG;
+                            v[REC_OPACITY] = G * dL_dalpha;
+                        }
+                    }
                 }
+                if (!__any_sync(FULL, active)) continue;
+                warp_transpose_reduce16(v, lane);
+                const int slot = lane >> 1;
+                if ((lane & 1) == 0 && slot <= REC_OPACITY) atomicAdd(rec + (size_t)lds32(a_id + j * 4) * RTG_REC + slot, v[0]);
             }
-            if (!__any_sync(0xffffffffu, active)) continue;
-            if (active) {
-                T = T / (1.f - alpha);
-                const float dch = alpha * T;
-                const float4 c = s_rgb[j];
-                float dL_dalpha;
-                accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0; lc0 = c.x;
-                accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1; lc1 = c.y;
-                accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2; lc2 = c.z;
-                dL_dalpha = (c.x - accum0) * dLp0;
-                dL_dalpha += (c.y - accum1) * dLp1;
-                dL_dalpha += (c.z - accum2) * dLp2;
-                v[REC_COLOR + 0] = dch * dLp0;
-                v[REC_COLOR + 1] = dch * dLp1;
-                v[REC_COLOR + 2] = dch * dLp2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                const float dL_dG = co.w * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                const float dG_ddely = -gdy * co.z - gdx * co.y;
-                v[REC_MEAN2D + 0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[REC_MEAN2D + 1] = dL_dG * dG_ddely * ddely_dy;
-                v[REC_CONIC + 0] = -0.5f * gdx * dx * dL_dG;
-                v[REC_CONIC + 1] = -0.5f * gdx * dy * dL_dG;
-                v[REC_CONIC + 2] = -0.5f * gdy * dy * dL_dG;
-                v[REC_OPACITY] = G * dL_dalpha;
-            }
-            warp_transpose_reduce16(v, lane);
-            const int slot = lane >> 1;
-            if ((lane & 1) == 0 && slot <= REC_OPACITY) atomicAdd(rec + (size_t)s_id[j] * RTG_REC + slot, v[0]);
         }
     }
 
@@ -320,10 +377,11 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
         const int gid = hit_image[pix_id];
         if (gid >= 0) {
             const float3 ray = pixel_ray(px, py, vp.focal_x, vp.focal_y, vp.cx, vp.cy);
-            const float4 h0 = g.hit0[gid], h1 = g.hit1[gid];
+            const float4 h0 = __ldg(g.hit + 2 * (size_t)gid), h1 = __ldg(g.hit + 2 * (size_t)gid + 1);
             const float3 nc = make_float3(h0.x, h0.y, h0.z);
             const float3 pc = make_float3(h1.x, h1.y, h1.z);
-            const float3 sc = make_float3(scales[3 * (size_t)gid], scales[3 * (size_t)gid + 1], scales[3 * (size_t)gid + 2]);
+            float3 sc = make_float3(0.f, 0.f, 0.f);
+            if (scales != nullptr) sc = make_float3(scales[3 * (size_t)gid], scales[3 * (size_t)gid + 1], scales[3 * (size_t)gid + 2]);
             const float scale_max = fmaxf(fmaxf(sc.x, sc.y), sc.z);  // no scale_modifier here (backward.cu:1009)
             const float num = pc.x * nc.x + pc.y * nc.y + pc.z * nc.z;
             const float ndotr = nc.x * ray.x + nc.y * ray.y + nc.z * ray.z;

@@ -1,0 +1,100 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in rtg_slam_b200/parallel.py: map broadcast, frame
+sharding, the flat gradient all-reduce, and that a replicated optimizer step keeps the ranks identical. Per-rank
+gradients come from the CPU oracle (different camera per frame), so the test also checks that the reduced gradient
+equals the single-process sum over the window."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rtg_slam_b200 import parallel, scene
+
+WINDOW = 3  # keyframes in the optimisation window
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _frame_grads(g, frame):
+    from oracle.splat_oracle import OracleRender
+    cam = scene.make_camera("tiny", c2w=scene.small_pose((0.5 * frame, -0.4 * frame, 0.2 * frame), (0.01 * frame, 0.0, 0.01 * frame)))
+    o = OracleRender(cam, g, precision="f32")
+    gr = o.backward(*scene.upstream_grads(cam, seed=5 + frame))
+    o.close()
+    return {k: torch.from_numpy(gr[k]) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P = 400
+        g_np = scene.surfel_room(P, seed=3) if rank == 0 else None
+        shapes = {"xyz": (P, 3), "opacity": (P, 1), "scales": (P, 3), "rotations": (P, 4), "shs": (P, 16, 3), "normal": (P, 3)}
+        t = {k: (torch.from_numpy(g_np[k]) if rank == 0 else torch.full(shapes[k], float("nan"))) for k in shapes}
+        parallel.broadcast_map(t)
+        parallel.assert_replicas_equal(list(t.values()))
+        g = {k: v.numpy() for k, v in t.items()}
+        mine = parallel.shard_frames(WINDOW)
+        fg = parallel.FlatGrads(P, "cpu")
+        for f in mine:
+            fg.accumulate(_frame_grads(g, f))
+        fg.allreduce()
+        # replicated optimizer step on the reduced gradient
+        params = [t["xyz"].clone().requires_grad_(True), t["shs"].clone().requires_grad_(True)]
+        opt = torch.optim.Adam([{"params": [params[0]], "lr": 1e-3}, {"params": [params[1]], "lr": 5e-4}], lr=0.0, eps=1e-15)
+        params[0].grad = fg.views["means3D"].clone()
+        params[1].grad = fg.views["shs"].clone()
+        opt.step()
+        parallel.assert_replicas_equal([p.detach() for p in params])
+        q.put((rank, mine, {k: v.clone().numpy() for k, v in fg.views.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_broadcast_shard_allreduce():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda x: x[0])
+    assert sorted(res[0][1] + res[1][1]) == list(range(WINDOW))  # every frame exactly once
+    assert abs(len(res[0][1]) - len(res[1][1])) <= 1
+    g = scene.surfel_room(400, seed=3)
+    total = None
+    for f in range(WINDOW):
+        gr = _frame_grads(g, f)
+        total = gr if total is None else {k: total[k] + gr[k] for k in gr}
+    for r in res:
+        for k in total:
+            ref = total[k].numpy().reshape(r[2][k].shape)
+            assert np.allclose(r[2][k], ref, rtol=1e-5, atol=1e-9), k
+    assert any(np.abs(v).max() > 0 for v in res[0][2].values())
+
+
+def test_shard_frames_and_flat_layout_single_process():
+    assert parallel.shard_frames(7, 3, 0) == [0, 3, 6] and parallel.shard_frames(7, 3, 2) == [2, 5]
+    assert parallel.shard_frames(2, 8, 5) == []
+    fg = parallel.FlatGrads(5, "cpu")
+    assert fg.views["shs"].shape == (5, 16, 3) and fg.views["rotations"].shape == (5, 4)
+    for v in fg.views.values():
+        assert v.data_ptr() % 16 == 0
+    fg.views["opacities"].fill_(2.0)
+    assert fg.flat.sum().item() == 10.0
+    assert fg.allreduce() is None  # no process group: no-op

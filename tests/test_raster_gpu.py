@@ -200,7 +200,7 @@ def test_full_size_properties(cuda_device):
     hit = r["hit_depth"][0]
     assert hit.max() < 1_000_000 and hit[up].min() >= -1
     assert (r["radii"][hit[(hit >= 0) & up]] > 0).all()  # a hit refers to a visible Gaussian
-    assert (r["hit_depth_weight"][0][(hit >= 0) & up] > 0).all()
+    assert (r["hit_depth_weight"][0][(hit >= 0) & up] >= 0).all()  # alpha*T; T may underflow to 0 behind many translucent splats
     assert ((r["depth"][0] > 0) == ((hit >= 0) & up)).mean() > 0.9999
     for k, v in r["grads"].items():
         assert np.isfinite(v).all(), k
