@@ -83,27 +83,46 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long
 __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P, const GeomState g, const int *__restrict__ radii,
                                                       const int *__restrict__ tile_mask, BinState b, long long R_cap,
                                                       const int *__restrict__ counters) {
+    __shared__ uint32_t s_excl[8][32], s_rect[8][32];
+    __shared__ float4 s_ga[8][32], s_gb[8][32];
     if (counters[2]) return;  // capacity overflow: render nothing, the caller retries with a larger buffer
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int r = radii[idx];
-    if (r <= 0) return;
-    const float4 s0 = g.splat[2 * (size_t)idx], s1 = g.splat[2 * (size_t)idx + 1];
-    int x0, y0, x1, y1;
-    tile_rect(make_float2(s0.x, s0.y), r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
-    const uint64_t key = ((uint64_t)__float_as_uint(s0.w) << 32) | (uint32_t)idx;
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            const int t = y * vp.tiles_x + x;
-            if (__ldg(tile_mask + t)) {
-                const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
-                // same (bit-identical) decision as the histogram pass in preprocess_fwd_kernel
-                if (rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
-                const uint32_t slot = atomicAdd(b.tile_fill + t, 1u);
-                const uint32_t begin = b.tile_offset[t];
-                if (slot < b.tile_offset[t + 1] - begin) b.keys[begin + slot] = key;  // never write outside the bucket
-            }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = idx < P ? radii[idx] : 0;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (r > 0) {
+        s0 = g.splat[2 * (size_t)idx];
+        s1 = g.splat[2 * (size_t)idx + 1];
+        tile_rect(make_float2(s0.x, s0.y), r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
+    }
+    const int npairs = (x1 - x0) * (y1 - y0);
+    const int incl = warp_incl_scan(npairs, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // warp-uniform
+    s_excl[w][lane] = (uint32_t)(incl - npairs);
+    s_rect[w][lane] = pack_rect(x0, y0, max(x1 - x0, 1));
+    s_ga[w][lane] = s0;  // x, y, q_cut, depth
+    s_gb[w][lane] = s1;  // conic, opacity
+    __syncwarp();
+    const int base = idx - lane;
+    for (int k = lane; k < total; k += 32) {
+        const int o = pair_owner(s_excl[w], (uint32_t)k);
+        const uint32_t local = (uint32_t)k - s_excl[w][o], rc = s_rect[w][o];
+        const uint32_t rw = rc >> 20;
+        const int x = (int)(rc & 1023u) + (int)(local % rw), y = (int)((rc >> 10) & 1023u) + (int)(local / rw);
+        const int t = y * vp.tiles_x + x;
+        if (__ldg(tile_mask + t)) {
+            const float4 ga = s_ga[w][o], gb = s_gb[w][o];
+            const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
+            // same (bit-identical) decision as the histogram pass in preprocess_fwd_kernel
+            if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
+            const uint32_t slot = atomicAdd(b.tile_fill + t, 1u);
+            const uint32_t begin = b.tile_offset[t];
+            if (slot < b.tile_offset[t + 1] - begin)  // never write outside the bucket
+                b.keys[begin + slot] = ((uint64_t)__float_as_uint(ga.w) << 32) | (uint32_t)(base + o);
         }
+    }
 }
 
 // ---------------------------------------------------------------- per-tile depth sort
@@ -120,9 +139,15 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *k, const int N, const int
                 const uint64_t x = k[a], y = k[c];
                 if ((x > y) == up) { k[a] = y; k[c] = x; }
             }
-            __syncthreads();
+            // Pair i touches keys inside the 64-key segment [64*(i/32), +63] whenever j <= 32, and thread t always
+            // handles the pairs i = t + m*nthreads, so a warp owns the same segments in every such sub-stage: a
+            // warp-level barrier is enough unless this or the next sub-stage crosses segments.
+            const int jn = (j > 1) ? (j >> 1) : size;  // stride of the next sub-stage
+            if (j > 32 || jn > 32) __syncthreads();
+            else __syncwarp();
         }
     }
+    __syncthreads();
 }
 
 __device__ __forceinline__ int next_pow2(int n) {

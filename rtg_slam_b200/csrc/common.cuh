@@ -157,6 +157,12 @@ __device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, f
     if (!(a > 0.f) || !(c > 0.f)) return false;  // not a proper conic: keep the reference's behaviour
     const float dxl = __fsub_rn(gx, x1), dxh = __fsub_rn(gx, x0), dyl = __fsub_rn(gy, y1), dyh = __fsub_rn(gy, y0);
     if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return false;
+    {
+        // quick accept: q at the rectangle point nearest to the centre already passes -> the minimum passes too
+        const float dx = fminf(dxh, fmaxf(dxl, 0.f)), dy = fminf(dyh, fmaxf(dyl, 0.f));
+        const float q0 = __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy))));
+        if (q0 <= q_cut) return false;
+    }
     const float nb_c = __fdiv_rn(-b, c), nb_a = __fdiv_rn(-b, a);
     float qmin;
     {
@@ -177,6 +183,26 @@ __device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, f
     }
     // the edge minimiser is exact up to rounding; shave a relative 1e-4 so that rounding can only keep, never cull
     return __fmul_rn(qmin, 0.9999f) > q_cut;
+}
+
+// Warp-cooperative expansion of per-lane tile rectangles into (owner lane, tile) pairs, so that the 32 lanes of a
+// warp share the pairs evenly instead of each lane looping over its own rectangle. `excl` / `rect` are the warp's
+// 32-entry shared arrays: exclusive prefix of the pair counts, and x0 | y0 << 10 | width << 20.
+__device__ __forceinline__ uint32_t pack_rect(int x0, int y0, int w) { return (uint32_t)x0 | ((uint32_t)y0 << 10) | ((uint32_t)w << 20); }
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+__device__ __forceinline__ int pair_owner(const uint32_t *excl, uint32_t k) {
+    int o = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+        if (excl[o + step] <= k) o += step;  // o + step <= 31 always
+    return o;
 }
 
 // explicit shared-state-space accesses with a precomputed 32-bit base (keeps address arithmetic out of the loops)

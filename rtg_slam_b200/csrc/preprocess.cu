@@ -106,29 +106,29 @@ __device__ __forceinline__ bool frustum_cull(const float3 p, const float *vm, co
     return (p_view.z <= 0.2f || p_proj.x < -1.3f || p_proj.x > 1.3f || p_proj.y < -1.3f || p_proj.y > 1.3f);
 }
 
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp, const int P, const int M,
-                                                             const float *__restrict__ means, const float *__restrict__ scales,
-                                                             const float *__restrict__ rots, const float *__restrict__ opac,
-                                                             const float *__restrict__ shs, const float *__restrict__ colors_precomp,
-                                                             const float *__restrict__ cov3D_precomp,
-                                                             const int *__restrict__ tile_mask, GeomState g,
-                                                             int *__restrict__ radii, uint32_t *__restrict__ tile_count,
-                                                             uint32_t *__restrict__ tile_touched) {
-    __shared__ float s_m[40];
-    if (threadIdx.x < 16) s_m[threadIdx.x] = vp.view[threadIdx.x];
-    else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
-    else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
-    __syncthreads();
+// Everything of the forward preprocess that concerns one Gaussian. Returns false if it is culled (radii = 0).
+// On success the splat / colour / surfel records are written and the tile rectangle is returned.
+struct SplatTiles {
+    float2 pix;
+    float3 conic;
+    float q_cut;
+    int x0, y0, x1, y1;
+};
+
+__device__ __forceinline__ bool preprocess_one(const ViewParams &vp, const int idx, const int M, const float *s_m,
+                                               const float *__restrict__ means, const float *__restrict__ scales,
+                                               const float *__restrict__ rots, const float *__restrict__ opac,
+                                               const float *__restrict__ shs, const float *__restrict__ colors_precomp,
+                                               const float *__restrict__ cov3D_precomp, const GeomState &g, int *__restrict__ radii,
+                                               SplatTiles &st) {
     const float *vm = s_m, *pm = s_m + 16;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
 
     const float3 p = make_float3(__ldg(means + 3 * (size_t)idx), __ldg(means + 3 * (size_t)idx + 1), __ldg(means + 3 * (size_t)idx + 2));
     float3 pv, pp;
     if (frustum_cull(p, vm, pm, pv, pp)) {
         if (vp.prefiltered) __trap();  // the reference traps as well (auxiliary.h:157-161)
         radii[idx] = 0;
-        return;
+        return false;
     }
 
     float c6[6];
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp
     ewa_A(pv, vm, vp.focal_x, vp.focal_y, vp.tanfovx, vp.tanfovy, A0, A1, t, txtz, tytz);
     cov2d_from(A0, A1, c6, AV0, AV1, ca, cb, cc);
     const float det = ca * cc - cb * cb;
-    if (det == 0.0f) { radii[idx] = 0; return; }
+    if (det == 0.0f) { radii[idx] = 0; return false; }
     const float det_inv = 1.f / det;
     const float3 conic = make_float3(cc * det_inv, -cb * det_inv, ca * det_inv);
     const float mid = 0.5f * (ca + cc);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp
                                    (float)((double)(pp.y * (float)vp.H) * 0.5 + (double)vp.cy));
     int x0, y0, x1, y1;
     tile_rect(pix, (int)my_radius, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
-    if ((x1 - x0) * (y1 - y0) == 0) { radii[idx] = 0; return; }
+    if ((x1 - x0) * (y1 - y0) == 0) { radii[idx] = 0; return false; }
 
     // colour
     float3 rgb;
@@ -226,21 +226,64 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp
     g.hit[2 * (size_t)idx] = h0;
     g.hit[2 * (size_t)idx + 1] = h1;
 
+    st.pix = pix; st.conic = conic; st.q_cut = q_cut;
+    st.x0 = x0; st.y0 = y0; st.x1 = x1; st.y1 = y1;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp, const int P, const int M,
+                                                             const float *__restrict__ means, const float *__restrict__ scales,
+                                                             const float *__restrict__ rots, const float *__restrict__ opac,
+                                                             const float *__restrict__ shs, const float *__restrict__ colors_precomp,
+                                                             const float *__restrict__ cov3D_precomp,
+                                                             const int *__restrict__ tile_mask, GeomState g,
+                                                             int *__restrict__ radii, uint32_t *__restrict__ tile_count,
+                                                             uint32_t *__restrict__ tile_touched) {
+    __shared__ float s_m[40];
+    __shared__ uint32_t s_excl[8][32], s_rect[8][32];
+    __shared__ float4 s_ga[8][32], s_gb[8][32];
+    if (threadIdx.x < 16) s_m[threadIdx.x] = vp.view[threadIdx.x];
+    else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+    SplatTiles st;
+    bool valid = false;
+    if (idx < P) valid = preprocess_one(vp, idx, M, s_m, means, scales, rots, opac, shs, colors_precomp, cov3D_precomp, g, radii, st);
+
     // Tile histogram over the masked-in tiles of the reference's rectangle (forward.cu:344-353), minus the tiles
     // in which no pixel can pass the alpha cut-off (exact test; such entries are skipped by every pixel of the
     // reference's render loop, so dropping them changes no output). Tiles that lose all their entries this way
-    // are flagged: the reference still renders them (hit maps -1, colour = background).
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            const int tt = y * vp.tiles_x + x;
-            if (__ldg(tile_mask + tt)) {
-                const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
-                if (rect_below_cutoff(pix.x, pix.y, conic.x, conic.y, conic.z, q_cut, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1)))
-                    tile_touched[tt] = 1u;
-                else
-                    atomicAdd(tile_count + tt, 1u);
-            }
+    // are flagged: the reference still renders them (hit maps -1, colour = background). The (Gaussian, tile)
+    // pairs of the warp's 32 Gaussians are shared evenly among its lanes.
+    const int npairs = valid ? (st.x1 - st.x0) * (st.y1 - st.y0) : 0;
+    const int incl = warp_incl_scan(npairs, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // warp-uniform
+    s_excl[w][lane] = (uint32_t)(incl - npairs);
+    if (valid) {
+        s_rect[w][lane] = pack_rect(st.x0, st.y0, st.x1 - st.x0);
+        s_ga[w][lane] = make_float4(st.pix.x, st.pix.y, st.q_cut, 0.f);
+        s_gb[w][lane] = make_float4(st.conic.x, st.conic.y, st.conic.z, 0.f);
+    }
+    __syncwarp();
+    for (int k = lane; k < total; k += 32) {
+        const int o = pair_owner(s_excl[w], (uint32_t)k);
+        const uint32_t local = (uint32_t)k - s_excl[w][o], rc = s_rect[w][o];
+        const uint32_t rw = rc >> 20;
+        const int x = (int)(rc & 1023u) + (int)(local % rw), y = (int)((rc >> 10) & 1023u) + (int)(local / rw);
+        const int tt = y * vp.tiles_x + x;
+        if (__ldg(tile_mask + tt)) {
+            const float4 ga = s_ga[w][o], gb = s_gb[w][o];
+            const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
+            if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1)))
+                tile_touched[tt] = 1u;
+            else
+                atomicAdd(tile_count + tt, 1u);
         }
+    }
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float *__restrict__ means, const float *__restrict__ view,
@@ -261,7 +304,7 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float *_
 // SH-path mean gradients; adds the depth-path mean / rotation gradients that the render backward
 // left in the record; writes every dense output exactly once (zeros for culled Gaussians) and
 // clears the record for the next call.
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
+__global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
                                                              const float *__restrict__ means, const float *__restrict__ scales,
                                                              const float *__restrict__ rots, const float *__restrict__ shs,
                                                              const float *__restrict__ cov3D_precomp, const int *__restrict__ radii,
