@@ -62,7 +62,12 @@ class _DeviceState:
         if self.pinned:
             return self.pinned.pop()
         t = torch.zeros(_lib.RTG_CNT_WORDS, dtype=torch.int32).pin_memory()
-        return t, torch.cuda.Event()
+        ev = torch.cuda.Event()
+        with torch.cuda.device(self.device):
+            ev.record()  # torch creates the cudaEvent_t lazily, at the first record(); the library needs the handle
+        if not ev.cuda_event:
+            raise RuntimeError("could not create a CUDA event for the capacity check")
+        return t, ev
 
     def put_pinned(self, item):
         self.pinned.append(item)
