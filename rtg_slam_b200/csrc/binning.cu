@@ -156,6 +156,10 @@ __device__ __forceinline__ int next_pow2(int n) {
     return N;
 }
 
+// One CTA per non-empty tile. Up to SORT_SMEM_KEYS keys are sorted in one go in 32 KB of shared memory. Longer
+// lists (rare: a few tiles in front of a dense surface) are sorted chunk by chunk and merged by rank: with chunk c
+// resident (sorted) in shared memory, every key of the tile adds the number of chunk-c keys below it (binary
+// search on chip; keys are unique), which is its final position once all chunks have been visited.
 __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(BinState b, const int *__restrict__ counters) {
     __shared__ uint64_t s_keys[SORT_SMEM_KEYS];
     if (counters[2]) return;
@@ -173,39 +177,46 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(BinState b, con
             bitonic_sort(s_keys, N, threadIdx.x, SORT_THREADS);
             for (int i = threadIdx.x; i < n; i += SORT_THREADS) out[i] = (uint32_t)s_keys[i];
             __syncthreads();
-        } else {
-            // Rare oversized bucket: sort in place in global memory (L2-resident). Elements past n of
-            // the padded power-of-two network are virtual +inf keys: a compare-exchange whose upper
-            // index is >= n can only matter when ascending (never moves +inf down) ...
-            // To stay simple and exact, run an odd-even merge on chunks instead:
-            //   1) sort chunks of SORT_SMEM_KEYS on chip, 2) merge chunks pairwise via rank computation.
-            const int nchunks = (n + SORT_SMEM_KEYS - 1) / SORT_SMEM_KEYS;
-            for (int c = 0; c < nchunks; c++) {
-                const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);
-                const int N = next_pow2(cn);
-                for (int i = threadIdx.x; i < N; i += SORT_THREADS) s_keys[i] = (i < cn) ? gk[c0 + i] : 0xffffffffffffffffull;
-                __syncthreads();
-                bitonic_sort(s_keys, N, threadIdx.x, SORT_THREADS);
-                for (int i = threadIdx.x; i < cn; i += SORT_THREADS) gk[c0 + i] = s_keys[i];
-                __syncthreads();
-            }
-            // rank of every key among all chunks = sum over chunks of (#keys smaller); keys are unique
+            continue;
+        }
+        const int nchunks = (n + SORT_SMEM_KEYS - 1) / SORT_SMEM_KEYS;
+        for (int c = 0; c < nchunks; c++) {  // sort every chunk in place
+            const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);
+            const int N = next_pow2(cn);
+            for (int i = threadIdx.x; i < N; i += SORT_THREADS) s_keys[i] = (i < cn) ? gk[c0 + i] : 0xffffffffffffffffull;
+            __syncthreads();
+            bitonic_sort(s_keys, N, threadIdx.x, SORT_THREADS);
+            for (int i = threadIdx.x; i < cn; i += SORT_THREADS) gk[c0 + i] = s_keys[i];
+            __syncthreads();
+        }
+        for (int c = 0; c < nchunks; c++) {  // accumulate ranks in `out` (used as scratch until the final permutation)
+            const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);
+            for (int i = threadIdx.x; i < cn; i += SORT_THREADS) s_keys[i] = gk[c0 + i];
+            __syncthreads();
             for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
-                const uint64_t key = gk[i];
-                int rank = 0;
-                for (int c = 0; c < nchunks; c++) {
-                    const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);
-                    int lo = 0, hi = cn;  // first index with gk[c0+idx] >= key
+                uint32_t r;
+                if (i >= c0 && i < c0 + cn) {
+                    r = (uint32_t)(i - c0);
+                } else {
+                    const uint64_t key = gk[i];
+                    int lo = 0, hi = cn;  // first index with s_keys[idx] >= key
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
-                        if (gk[c0 + mid] < key) lo = mid + 1; else hi = mid;
+                        if (s_keys[mid] < key) lo = mid + 1; else hi = mid;
                     }
-                    rank += lo;
+                    r = (uint32_t)lo;
                 }
-                out[rank] = (uint32_t)key;
+                out[i] = (c == 0) ? r : out[i] + r;
             }
             __syncthreads();
         }
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) gk[i] = ((uint64_t)out[i] << 32) | (uint32_t)gk[i];  // (rank, id)
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+            const uint64_t v = gk[i];
+            out[(uint32_t)(v >> 32)] = (uint32_t)v;
+        }
+        __syncthreads();
     }
 }
 

@@ -165,7 +165,7 @@ int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const floa
     cudaError_t e = cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)b.tile_offset - (char *)b.tile_count), s);
     if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward memset: ") + cudaGetErrorString(e));
     rtg::launch_preprocess_fwd(vp, P, M, means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp, tile_mask, g,
-                               radii, b.tile_count, b.tile_touched, s);
+                               radii, b.tile_count, b.tile_touched, b.vis_count, s);
     rtg::launch_tile_scan(b, T, R_cap, counters, counters_host, s);
     if (scan_done_event) {
         e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(scan_done_event), s);
@@ -210,7 +210,7 @@ int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const flo
     // backward reads the same device counters the forward wrote.
     rtg::launch_render_bwd(vp, g, b, img, counters, means3D, scales, rotations, final_T, hit_image, dL_dcolor, dL_ddepth,
                            grad2d_scratch, s);
-    rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, radii, g, grad2d_scratch, dL_dmeans3D,
+    rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, radii, g, b.vis_count, grad2d_scratch, dL_dmeans3D,
                                dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, s);
     return check_launch("rtg_splat_backward");
 }

@@ -30,12 +30,14 @@ struct GeomState {
     float4 *rgb_flags; // [P]   SH colour (clamped at 0) + clamp bits (int in .w)
     float4 *hit;       // [2P]  [2i]   = view-space normal (xyz), scale_max*scale_modifier
                        //       [2i+1] = view-space centre (xyz), normal axis (int in .w)
+    uint32_t *vis_list; // [P]  ids of the Gaussians that survived the preprocess (count in BinState::vis_count)
 };
 
 struct BinState {
     uint32_t *tile_count;   // [T]   instances per tile
     uint32_t *tile_fill;    // [T]   scatter cursors
     uint32_t *tile_touched; // [T]   1 if a Gaussian's rectangle covered the tile but the exact test culled it
+    uint32_t *vis_count;    // [1]   number of entries of GeomState::vis_list
     uint32_t *tile_offset;  // [T+1] exclusive scan of tile_count
     uint32_t *active;       // [T]   ascending ids of tiles with a non-empty list
     uint64_t *keys;         // [R_cap] (depth bits << 32 | gaussian id), bucketed by tile
@@ -61,6 +63,7 @@ static inline GeomState geom_from(void *ws, size_t P, size_t *bytes = nullptr) {
     g.splat = carve<float4>(p, 2 * P);
     g.rgb_flags = carve<float4>(p, P);
     g.hit = carve<float4>(p, 2 * P);
+    g.vis_list = carve<uint32_t>(p, P);
     if (bytes) *bytes = (size_t)(p - reinterpret_cast<char *>(ws));
     return g;
 }
@@ -68,10 +71,11 @@ static inline GeomState geom_from(void *ws, size_t P, size_t *bytes = nullptr) {
 static inline BinState bin_from(void *ws, size_t T, size_t R_cap, size_t *bytes = nullptr) {
     char *p = reinterpret_cast<char *>(ws);
     BinState b;
-    // tile_count, tile_fill and tile_touched are adjacent: one memset clears all three
+    // tile_count, tile_fill, tile_touched and vis_count are adjacent: one memset clears them all
     b.tile_count = carve<uint32_t>(p, T);
     b.tile_fill = carve<uint32_t>(p, T);
     b.tile_touched = carve<uint32_t>(p, T);
+    b.vis_count = carve<uint32_t>(p, 1);
     b.tile_offset = carve<uint32_t>(p, T + 1);
     b.active = carve<uint32_t>(p, T);
     b.keys = carve<uint64_t>(p, R_cap);

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp
                                                              const float *__restrict__ cov3D_precomp,
                                                              const int *__restrict__ tile_mask, GeomState g,
                                                              int *__restrict__ radii, uint32_t *__restrict__ tile_count,
-                                                             uint32_t *__restrict__ tile_touched) {
+                                                             uint32_t *__restrict__ tile_touched, uint32_t *__restrict__ vis_count) {
     __shared__ float s_m[40];
     __shared__ uint32_t s_excl[8][32], s_rect[8][32];
     __shared__ float4 s_ga[8][32], s_gb[8][32];
@@ -258,6 +258,15 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp
     // reference's render loop, so dropping them changes no output). Tiles that lose all their entries this way
     // are flagged: the reference still renders them (hit maps -1, colour = background). The (Gaussian, tile)
     // pairs of the warp's 32 Gaussians are shared evenly among its lanes.
+    {   // compact list of the surviving Gaussians (used by the backward preprocess); warp-aggregated append
+        const uint32_t vb = __ballot_sync(0xffffffffu, valid);
+        if (vb) {
+            uint32_t basep = 0;
+            if (lane == 0) basep = atomicAdd(vis_count, (uint32_t)__popc(vb));
+            basep = __shfl_sync(0xffffffffu, basep, 0);
+            if (valid) g.vis_list[basep + __popc(vb & ((1u << lane) - 1u))] = (uint32_t)idx;
+        }
+    }
     const int npairs = valid ? (st.x1 - st.x0) * (st.y1 - st.y0) : 0;
     const int incl = warp_incl_scan(npairs, lane);
     const int total = __shfl_sync(0xffffffffu, incl, 31);
@@ -304,49 +313,45 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float *_
 // SH-path mean gradients; adds the depth-path mean / rotation gradients that the render backward
 // left in the record; writes every dense output exactly once (zeros for culled Gaussians) and
 // clears the record for the next call.
-__global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
-                                                             const float *__restrict__ means, const float *__restrict__ scales,
-                                                             const float *__restrict__ rots, const float *__restrict__ shs,
-                                                             const float *__restrict__ cov3D_precomp, const int *__restrict__ radii,
-                                                             const GeomState g, float *__restrict__ rec,
-                                                             float *__restrict__ dL_dmeans, float *__restrict__ dL_dsh,
-                                                             float *__restrict__ dL_dcolors, float *__restrict__ dL_dopacity,
-                                                             float *__restrict__ dL_dscales, float *__restrict__ dL_drot,
-                                                             float *__restrict__ dL_dcov3D, float *__restrict__ dL_dmeans2D) {
-    __shared__ float s_m[40];
-    if (threadIdx.x < 16) s_m[threadIdx.x] = vp.view[threadIdx.x];
-    else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
-    else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
-    __syncthreads();
+struct BwdOut {
+    float *dL_dmeans, *dL_dsh, *dL_dcolors, *dL_dopacity, *dL_dscales, *dL_drot, *dL_dcov3D, *dL_dmeans2D;
+};
+
+// zeros for a culled Gaussian (the reference zero-fills all gradient tensors first, rasterize_points.cu:195-203)
+__device__ __forceinline__ void bwd_zero(const int idx, const int M, const bool has_sh, const bool has_sr, const BwdOut &o) {
+    const size_t i3 = 3 * (size_t)idx;
+    o.dL_dmeans[i3] = 0.f; o.dL_dmeans[i3 + 1] = 0.f; o.dL_dmeans[i3 + 2] = 0.f;
+    o.dL_dopacity[idx] = 0.f;
+    if (has_sr) {
+        o.dL_dscales[i3] = 0.f; o.dL_dscales[i3 + 1] = 0.f; o.dL_dscales[i3 + 2] = 0.f;
+        reinterpret_cast<float4 *>(o.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (has_sh) {
+        if (M == 16) {
+            float4 *p = reinterpret_cast<float4 *>(o.dL_dsh + (size_t)idx * 48);
+#pragma unroll
+            for (int i = 0; i < 12; i++) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = 0; i < 3 * M; i++) o.dL_dsh[(size_t)idx * 3 * M + i] = 0.f;
+        }
+    }
+    if (o.dL_dcolors) { o.dL_dcolors[i3] = 0.f; o.dL_dcolors[i3 + 1] = 0.f; o.dL_dcolors[i3 + 2] = 0.f; }
+    if (o.dL_dcov3D)
+        for (int i = 0; i < 6; i++) o.dL_dcov3D[6 * (size_t)idx + i] = 0.f;
+    if (o.dL_dmeans2D) { o.dL_dmeans2D[i3] = 0.f; o.dL_dmeans2D[i3 + 1] = 0.f; o.dL_dmeans2D[i3 + 2] = 0.f; }
+}
+
+__device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx, const int M, const float *s_m,
+                                            const float *__restrict__ means, const float *__restrict__ scales,
+                                            const float *__restrict__ rots, const float *__restrict__ shs,
+                                            const float *__restrict__ cov3D_precomp, const GeomState &g, float *__restrict__ rec,
+                                            const BwdOut &o) {
     const float *vm = s_m, *pj = s_m + 16;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
     const size_t i3 = 3 * (size_t)idx;
     const bool has_sh = (shs != nullptr);
     const bool has_sr = (cov3D_precomp == nullptr);
-
-    if (!(radii[idx] > 0)) {
-        dL_dmeans[i3] = 0.f; dL_dmeans[i3 + 1] = 0.f; dL_dmeans[i3 + 2] = 0.f;
-        dL_dopacity[idx] = 0.f;
-        if (has_sr) {
-            dL_dscales[i3] = 0.f; dL_dscales[i3 + 1] = 0.f; dL_dscales[i3 + 2] = 0.f;
-            reinterpret_cast<float4 *>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (has_sh) {
-            if (M == 16) {
-                float4 *o = reinterpret_cast<float4 *>(dL_dsh + (size_t)idx * 48);
-#pragma unroll
-                for (int i = 0; i < 12; i++) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                for (int i = 0; i < 3 * M; i++) dL_dsh[(size_t)idx * 3 * M + i] = 0.f;
-            }
-        }
-        if (dL_dcolors) { dL_dcolors[i3] = 0.f; dL_dcolors[i3 + 1] = 0.f; dL_dcolors[i3 + 2] = 0.f; }
-        if (dL_dcov3D)
-            for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = 0.f;
-        if (dL_dmeans2D) { dL_dmeans2D[i3] = 0.f; dL_dmeans2D[i3 + 1] = 0.f; dL_dmeans2D[i3 + 2] = 0.f; }
-        return;
-    }
+    float *dL_dmeans = o.dL_dmeans, *dL_dsh = o.dL_dsh, *dL_dcolors = o.dL_dcolors, *dL_dopacity = o.dL_dopacity,
+          *dL_dscales = o.dL_dscales, *dL_drot = o.dL_drot, *dL_dcov3D = o.dL_dcov3D, *dL_dmeans2D = o.dL_dmeans2D;
 
     // consume + clear the gradient record
     float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)idx * RTG_REC);
@@ -533,15 +538,36 @@ __global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(const ViewParams
     if (dL_dmeans2D) { dL_dmeans2D[i3] = g2x; dL_dmeans2D[i3 + 1] = g2y; dL_dmeans2D[i3 + 2] = 0.f; }
 }
 
+
+// Two duties per CTA: (1) zero the gradients of the culled Gaussians of its own index range (light, streaming);
+// (2) run the full backward for one slice of the compact visible list built by the forward preprocess, so that the
+// register-heavy path executes with full warps instead of ~40 % of the lanes.
+__global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
+                                                                const float *__restrict__ means, const float *__restrict__ scales,
+                                                                const float *__restrict__ rots, const float *__restrict__ shs,
+                                                                const float *__restrict__ cov3D_precomp, const int *__restrict__ radii,
+                                                                const GeomState g, const uint32_t *__restrict__ vis_count,
+                                                                float *__restrict__ rec, const BwdOut o) {
+    __shared__ float s_m[40];
+    if (threadIdx.x < 16) s_m[threadIdx.x] = vp.view[threadIdx.x];
+    else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < P && !(radii[idx] > 0)) bwd_zero(idx, M, shs != nullptr, cov3D_precomp == nullptr, o);
+    const uint32_t V = *vis_count;
+    if ((uint32_t)idx < V) bwd_visible(vp, (int)g.vis_list[idx], M, s_m, means, scales, rots, shs, cov3D_precomp, g, rec, o);
+}
+
 // ------------------------------------------------------------------ launchers
 void launch_preprocess_fwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
                            const float *opac, const float *shs, const float *colors_precomp, const float *cov3D_precomp,
                            const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, uint32_t *tile_touched,
-                           cudaStream_t s) {
+                           uint32_t *vis_count, cudaStream_t s) {
     if (P <= 0) return;
     ProfScope ps(K_PREPROCESS_FWD, s);
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, opac, shs, colors_precomp, cov3D_precomp,
-                                                          tile_mask, g, radii, tile_count, tile_touched);
+                                                          tile_mask, g, radii, tile_count, tile_touched, vis_count);
 }
 
 void launch_mark_visible(int P, const float *means, const float *view, const float *proj, uint8_t *present, cudaStream_t s) {
@@ -550,14 +576,13 @@ void launch_mark_visible(int P, const float *means, const float *view, const flo
 }
 
 void launch_preprocess_bwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
-                           const float *shs, const float *cov3D_precomp, const int *radii, const GeomState &g, float *rec,
-                           float *dL_dmeans, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
-                           float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s) {
+                           const float *shs, const float *cov3D_precomp, const int *radii, const GeomState &g,
+                           const uint32_t *vis_count, float *rec, float *dL_dmeans, float *dL_dsh, float *dL_dcolors,
+                           float *dL_dopacity, float *dL_dscales, float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s) {
     if (P <= 0) return;
     ProfScope ps(K_PREPROCESS_BWD, s);
-    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, shs, cov3D_precomp, radii, g, rec,
-                                                          dL_dmeans, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drot,
-                                                          dL_dcov3D, dL_dmeans2D);
+    BwdOut o{dL_dmeans, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drot, dL_dcov3D, dL_dmeans2D};
+    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, shs, cov3D_precomp, radii, g, vis_count, rec, o);
 }
 
 }  // namespace rtg

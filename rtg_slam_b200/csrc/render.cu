@@ -203,43 +203,70 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
 
 // ------------------------------------------------------------------ backward
 
-// Sum 16 per-lane values across the warp with a transposing butterfly: after the call, value k's
-// total sits in v[0] of lanes 2k and 2k+1.
-__device__ __forceinline__ void warp_transpose_reduce16(float v[16], const int lane) {
-    {
-        const bool hi = lane & 16;
+// Sum 9 per-lane values across the warp with a transposing butterfly (12 shuffles instead of 45): at every step a
+// lane keeps one half of its values and trades the other half with its partner. Afterwards value k's total sits in
+// lane kLaneOfValue[k]; `slot_of_lane` returns the value index a lane ends up holding (or -1).
+//   step xor 16: lanes with bit4 = 0 keep v0..v4, bit4 = 1 keep v5..v8            (5 shuffles)
+//   step xor  8: of those, bit3 = 0 keeps the first ceil(half), bit3 = 1 the rest   (3 shuffles)
+//   step xor  4: (2 shuffles), step xor 2: (1 shuffle), step xor 1: plain add        (1 shuffle)
+__device__ __forceinline__ float warp_reduce9(const float v[9], const int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    // after xor 16: a[0..4]; lanes b4=0: sums of v0..v4, lanes b4=1: sums of v5..v8 (a[4] unused there)
+    float a[5];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float send = hi ? v[i] : v[i + 8];
-            const float keep = hi ? v[i + 8] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
-        }
+    for (int i = 0; i < 5; i++) {
+        const float hi_val = (i < 4) ? v[5 + i] : 0.f;
+        const float send = b4 ? v[i] : hi_val;
+        const float keep = b4 ? hi_val : v[i];
+        a[i] = keep + __shfl_xor_sync(FULL, send, 16);
     }
-    {
-        const bool hi = lane & 8;
+    // after xor 8: c[0..2]; b3=0 keeps a0..a2, b3=1 keeps a3..a4
+    float c[3];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float send = hi ? v[i] : v[i + 4];
-            const float keep = hi ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
-        }
+    for (int i = 0; i < 3; i++) {
+        const float hi_val = (i < 2) ? a[3 + i] : 0.f;
+        const float send = b3 ? a[i] : hi_val;
+        const float keep = b3 ? hi_val : a[i];
+        c[i] = keep + __shfl_xor_sync(FULL, send, 8);
     }
-    {
-        const bool hi = lane & 4;
+    // after xor 4: d[0..1]; b2=0 keeps c0..c1, b2=1 keeps c2
+    float d[2];
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const float send = hi ? v[i] : v[i + 2];
-            const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 4);
-        }
+    for (int i = 0; i < 2; i++) {
+        const float hi_val = (i < 1) ? c[2 + i] : 0.f;
+        const float send = b2 ? c[i] : hi_val;
+        const float keep = b2 ? hi_val : c[i];
+        d[i] = keep + __shfl_xor_sync(FULL, send, 4);
     }
+    // after xor 2: b1=0 keeps d0, b1=1 keeps d1
+    float e;
     {
-        const bool hi = lane & 2;
-        const float send = hi ? v[0] : v[1];
-        const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
+        const float send = b1 ? d[0] : d[1];
+        const float keep = b1 ? d[1] : d[0];
+        e = keep + __shfl_xor_sync(FULL, send, 2);
     }
-    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+    e += __shfl_xor_sync(FULL, e, 1);
+    return e;
+}
+
+// value index held by a lane after warp_reduce9 (-1: padding)
+__device__ __forceinline__ int reduce9_slot(const int lane) {
+    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+    // level sizes: 9 -> (5 | 4) -> (3 | 2) -> (2 | 1) -> (1 | 1)
+    int base = b4 ? 5 : 0, cnt = b4 ? 4 : 5;           // values [base, base+cnt)
+    {   // xor 8: first 3 stay with b3=0, rest with b3=1
+        const int lo = 3;
+        if (b3) { base += lo; cnt -= lo; } else { cnt = min(cnt, lo); }
+    }
+    {   // xor 4: first 2 stay with b2=0, rest with b2=1
+        const int lo = 2;
+        if (b2) { base += lo; cnt -= lo; } else { cnt = min(cnt, lo); }
+    }
+    {   // xor 2: first 1 stays with b1=0, rest with b1=1
+        const int lo = 1;
+        if (b1) { base += lo; cnt -= lo; } else { cnt = min(cnt, lo); }
+    }
+    return cnt > 0 ? base : -1;
 }
 
 __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b, const ImgState img,
@@ -293,6 +320,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
 
     float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+    const int my_slot = (lane & 1) ? -1 : reduce9_slot(lane);  // lanes 2k and 2k+1 hold the same total: one of them adds it
     const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
 
     const int rounds = ((int)m + BATCH - 1) / BATCH;
@@ -322,9 +350,9 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
                 const int j = (c << 5) + __ffs(bits) - 1;
                 bits &= bits - 1;
                 const uint32_t pos = m - 1 - (uint32_t)(i * BATCH + j);
-                float v[16];
+                float v[9];
 #pragma unroll
-                for (int k = 0; k < 16; k++) v[k] = 0.f;
+                for (int k = 0; k < 9; k++) v[k] = 0.f;
                 bool active = pos < last_contributor;
                 if (active) {
                     const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
@@ -365,9 +393,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
                     }
                 }
                 if (!__any_sync(FULL, active)) continue;
-                warp_transpose_reduce16(v, lane);
-                const int slot = lane >> 1;
-                if ((lane & 1) == 0 && slot <= REC_OPACITY) atomicAdd(rec + (size_t)lds32(a_id + j * 4) * RTG_REC + slot, v[0]);
+                const float tot = warp_reduce9(v, lane);
+                if (my_slot >= 0) atomicAdd(rec + (size_t)lds32(a_id + j * 4) * RTG_REC + my_slot, tot);
             }
         }
     }

@@ -268,6 +268,27 @@ def random_blobs(P: int, seed: int = 7, sh_coeffs: int = 16, depth=(0.4, 5.0), d
     }
 
 
+def dense_blobs(P: int, seed: int = 21, sh_coeffs: int = 16, dtype=np.float32):
+    """Translucent Gaussians packed inside a narrow frustum: very long per-tile lists (stress for the per-tile sort
+    and for pixels that never reach an opaque hit)."""
+    rng = np.random.default_rng(seed)
+    z = rng.uniform(1.0, 3.0, P)
+    xyz = np.stack([rng.uniform(-0.45, 0.45, P) * z, rng.uniform(-0.35, 0.35, P) * z, z], axis=1)
+    q = rng.normal(size=(P, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    scales = np.exp(rng.uniform(math.log(0.01), math.log(0.08), (P, 3)))
+    opacity = rng.uniform(0.02, 0.3, (P, 1))
+    shs = np.zeros((P, sh_coeffs, 3))
+    shs[:, 0] = rng.uniform(0.0, 1.0, (P, 3)) / SH_C0 - 0.5 / SH_C0
+    if sh_coeffs > 1:
+        shs[:, 1:] = rng.normal(0, 0.1, (P, sh_coeffs - 1, 3))
+    return {
+        "xyz": np.ascontiguousarray(xyz.astype(dtype)), "opacity": np.ascontiguousarray(opacity.astype(dtype)),
+        "scales": np.ascontiguousarray(scales.astype(dtype)), "rotations": np.ascontiguousarray(q.astype(dtype)),
+        "shs": np.ascontiguousarray(shs.astype(dtype)), "normal": np.zeros((P, 3), dtype=dtype),
+    }
+
+
 def random_tile_mask(cam: Camera, keep: float = 0.5, seed: int = 11) -> np.ndarray:
     rng = np.random.default_rng(seed)
     th, tw = cam.tile_grid

@@ -31,7 +31,8 @@ def check_against_oracle(cam, g, dev, mask=None, label="", **over):
     ours = helpers.run_ours(cam, g, dev, tile_mask=mask, grads=grads, **over)
     o = OracleRender(cam, g, tile_mask=mask, precision="f32", tie_eps=1e-4, **over)
     st = helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, tol=1e-4, label=label)
-    assert st["radii_mismatch"] == 0, st
+    # ceil(3 sigma) may differ by one pixel for a Gaussian whose extent is within rounding of an integer
+    assert st["radii_mismatch"] <= max(0, int(1e-5 * g["xyz"].shape[0])), st
     og = o.backward(*grads)
     for k in GRADS:
         e = helpers.rel_err(ours["grads"][k], og[k])
@@ -91,6 +92,17 @@ def test_thresholds_variants(cuda_device):
     g = scene.random_blobs(1500, seed=12)
     check_against_oracle(cam, g, cuda_device, label="thr", opaque_threshold=0.3, depth_threshold=0.5,
                          normal_threshold=float(np.cos(np.deg2rad(30.0))), color_sigma=2.0, T_threshold=1e-3)
+
+
+@pytest.mark.parametrize("P", [30_000, 250_000])
+def test_oversized_tile_lists(cuda_device, P):
+    """Tile lists longer than the on-chip sort capacity (4096 keys; then 8192; then chunked): the slow paths of the per-tile sort."""
+    cam = scene.make_camera("tiny")
+    g = scene.dense_blobs(P, seed=21)
+    ours, o = check_against_oracle(cam, g, cuda_device, label=f"oversized{P}")
+    _, rg = o.binning()
+    longest = int((rg[:, 1] - rg[:, 0]).max())
+    assert longest > (2 * 4096 if P < 50_000 else 4 * 8192), longest  # ours are shorter (exact culling), still past the limits
 
 
 def test_edge_cases(cuda_device):
