@@ -16,65 +16,75 @@ namespace rtg {
 // ---------------------------------------------------------------- tile scan (single CTA)
 __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long long R_cap, int *__restrict__ counters,
                                                          int *__restrict__ counters_host) {
-    __shared__ uint32_t s_warp[32], s_warp_act[32];
-    __shared__ uint32_t s_carry, s_carry_act, s_max;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry, s_max, s_nact;
+    __shared__ uint32_t s_cls[66];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_carry_act = 0; s_max = 0; }
+    if (tid == 0) { s_carry = 0; s_max = 0; s_nact = 0; }
+    if (tid < 66) s_cls[tid] = 0;
     __syncthreads();
-    uint32_t local_max = 0;
+    uint32_t local_max = 0, local_act = 0;
+    // (1) exclusive scan of the histogram -> tile offsets; (2) histogram of work classes for the launch order
     for (int base = 0; base < T; base += 1024) {
         const int i = base + tid;
         const uint32_t c = (i < T) ? b.tile_count[i] : 0u;
-        const uint32_t a = c > 0 ? 1u : 0u;
         local_max = max(local_max, c);
-        uint32_t v = c, va = a;
+        local_act += (c > 0);
+        uint32_t v = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, v, o), na = __shfl_up_sync(0xffffffffu, va, o);
-            if (lane >= o) { v += n; va += na; }
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
         }
-        if (lane == 31) { s_warp[wid] = v; s_warp_act[wid] = va; }
+        if (lane == 31) s_warp[wid] = v;
         __syncthreads();
         if (wid == 0) {
-            uint32_t w = s_warp[lane], wa = s_warp_act[lane];
+            uint32_t w = s_warp[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, w, o), na = __shfl_up_sync(0xffffffffu, wa, o);
-                if (lane >= o) { w += n; wa += na; }
+                const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
             }
-            s_warp[lane] = w; s_warp_act[lane] = wa;
+            s_warp[lane] = w;
         }
         __syncthreads();
-        const uint32_t carry = s_carry, carry_a = s_carry_act;
-        const uint32_t incl = v + (wid > 0 ? s_warp[wid - 1] : 0u) + carry;
-        const uint32_t incl_a = va + (wid > 0 ? s_warp_act[wid - 1] : 0u) + carry_a;
+        const uint32_t incl = v + (wid > 0 ? s_warp[wid - 1] : 0u) + s_carry;
         if (i < T) {
             b.tile_offset[i] = incl - c;
-            if (a) b.active[incl_a - 1] = (uint32_t)i;
+            // class 0 = longest lists (>= 4032 entries) ... class 63 = 1..63 entries, class 64 = empty tiles
+            const int cls = (c == 0) ? 64 : 63 - (int)min(63u, c >> 6);
+            atomicAdd(&s_cls[cls], 1u);
         }
         __syncthreads();
-        if (tid == 1023) { s_carry = incl; s_carry_act = incl_a; }
+        if (tid == 1023) s_carry = incl;
         __syncthreads();
     }
-    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 16));
-    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 8));
-    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 4));
-    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 2));
-    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 1));
-    if (lane == 0) atomicMax(&s_max, local_max);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+        local_act += __shfl_xor_sync(0xffffffffu, local_act, o);
+    }
+    if (lane == 0) { atomicMax(&s_max, local_max); atomicAdd(&s_nact, local_act); }
     __syncthreads();
+    // Launch order of the tiles: longest lists first (the block scheduler hands out CTAs in index order, so this
+    // is longest-processing-time-first scheduling), empty tiles last. Order inside a class is irrelevant.
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int k = 0; k < 65; k++) { const uint32_t n = s_cls[k]; s_cls[k] = run; run += n; }
+    }
+    __syncthreads();
+    for (int i = tid; i < T; i += 1024) {
+        const uint32_t c = b.tile_count[i];
+        const int cls = (c == 0) ? 64 : 63 - (int)min(63u, c >> 6);
+        b.active[atomicAdd(&s_cls[cls], 1u)] = (uint32_t)i;
+    }
     if (tid == 0) {
         const uint32_t R = s_carry;
         b.tile_offset[T] = R;
-        counters[0] = (int)R;
-        counters[1] = (int)s_carry_act;
-        counters[2] = ((long long)R > R_cap) ? 1 : 0;
-        counters[3] = (int)s_max;
+        const int ov = ((long long)R > R_cap) ? 1 : 0;
+        counters[0] = (int)R; counters[1] = (int)s_nact; counters[2] = ov; counters[3] = (int)s_max;
         if (counters_host) {
-            counters_host[0] = (int)R;
-            counters_host[1] = (int)s_carry_act;
-            counters_host[2] = ((long long)R > R_cap) ? 1 : 0;
-            counters_host[3] = (int)s_max;
+            counters_host[0] = (int)R; counters_host[1] = (int)s_nact; counters_host[2] = ov; counters_host[3] = (int)s_max;
         }
     }
 }

@@ -39,7 +39,7 @@ struct BinState {
     uint32_t *tile_touched; // [T]   1 if a Gaussian's rectangle covered the tile but the exact test culled it
     uint32_t *vis_count;    // [1]   number of entries of GeomState::vis_list
     uint32_t *tile_offset;  // [T+1] exclusive scan of tile_count
-    uint32_t *active;       // [T]   ascending ids of tiles with a non-empty list
+    uint32_t *active;       // [T]   launch order of the tiles: longest list first, empty tiles last
     uint64_t *keys;         // [R_cap] (depth bits << 32 | gaussian id), bucketed by tile
     uint32_t *point_list;   // [R_cap] gaussian ids, per tile front-to-back
 };

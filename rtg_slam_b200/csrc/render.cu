@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
     __shared__ int s_id[BATCH];
     __shared__ uint32_t s_mask[BATCH];
 
-    const int tile = blockIdx.x;
+    const int tile = (int)b.active[blockIdx.x];  // longest lists first
     int px, py;
     bool inside;
     pixel_of(vp, tile, px, py, inside);
@@ -269,7 +269,7 @@ __device__ __forceinline__ int reduce9_slot(const int lane) {
     return cnt > 0 ? base : -1;
 }
 
-__global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b, const ImgState img,
+__global__ void __launch_bounds__(256, 4) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b, const ImgState img,
                                                          const int *__restrict__ counters, const float *__restrict__ means,
                                                          const float *__restrict__ scales, const float *__restrict__ rots,
                                                          const float *__restrict__ final_T, const int *__restrict__ hit_image,
@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
     __shared__ uint32_t s_max[8];
 
     if (counters[2]) return;
-    const int tile = blockIdx.x;
+    if ((int)blockIdx.x >= counters[1]) return;  // empty tiles sit at the end of the launch order
+    const int tile = (int)b.active[blockIdx.x];
     const uint32_t start = b.tile_offset[tile];
     const int n = (int)(b.tile_offset[tile + 1] - start);
     if (n == 0) return;
@@ -364,7 +365,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
                         const float alpha = fminf(0.99f, s1.w * G);
                         active = !(alpha < 1.0f / 255.0f);
                         if (active) {
-                            T = T / (1.f - alpha);
+                            const float inv_1ma = __frcp_rn(1.f - alpha);
+                            T = T * inv_1ma;
                             const float dch = alpha * T;
                             const float4 col = lds128(a_rgb + j * 16);
                             accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0; lc0 = col.x;
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const ViewParams vp, co
                             v[REC_COLOR + 2] = dch * dLp2;
                             dL_dalpha *= T;
                             last_alpha = alpha;
-                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                            if (bg_dot_dpixel != 0.f) dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
                             const float dL_dG = s1.w * dL_dalpha;
                             const float gdx = G * dx, gdy = G * dy;
                             const float dG_ddelx = -gdx * s1.x - gdy * s1.y;
