@@ -318,7 +318,8 @@ struct BwdOut {
 };
 
 // zeros for a culled Gaussian (the reference zero-fills all gradient tensors first, rasterize_points.cu:195-203)
-__device__ __forceinline__ void bwd_zero(const int idx, const int M, const bool has_sh, const bool has_sr, const BwdOut &o) {
+__device__ __forceinline__ void bwd_zero(const int idx, const int M, const bool has_sh, const bool has_sr, const BwdOut &o,
+                                         const bool sh_done) {
     const size_t i3 = 3 * (size_t)idx;
     o.dL_dmeans[i3] = 0.f; o.dL_dmeans[i3 + 1] = 0.f; o.dL_dmeans[i3 + 2] = 0.f;
     o.dL_dopacity[idx] = 0.f;
@@ -326,7 +327,7 @@ __device__ __forceinline__ void bwd_zero(const int idx, const int M, const bool 
         o.dL_dscales[i3] = 0.f; o.dL_dscales[i3 + 1] = 0.f; o.dL_dscales[i3 + 2] = 0.f;
         reinterpret_cast<float4 *>(o.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (has_sh) {
+    if (has_sh && !sh_done) {
         if (M == 16) {
             float4 *p = reinterpret_cast<float4 *>(o.dL_dsh + (size_t)idx * 48);
 #pragma unroll
@@ -339,6 +340,89 @@ __device__ __forceinline__ void bwd_zero(const int idx, const int M, const bool 
     if (o.dL_dcov3D)
         for (int i = 0; i < 6; i++) o.dL_dcov3D[6 * (size_t)idx + i] = 0.f;
     if (o.dL_dmeans2D) { o.dL_dmeans2D[i3] = 0.f; o.dL_dmeans2D[i3 + 1] = 0.f; o.dL_dmeans2D[i3 + 2] = 0.f; }
+}
+
+// SH part of the backward (computeColorFromSH, backward.cu:152-268): dL/dsh and the view-direction term of dL/dmean.
+// Kept out of line and executed before the covariance chain so that the 48 SH coefficients and the 16 basis
+// weights are not live at the same time as the covariance intermediates.
+__device__ __noinline__ float3 bwd_sh(const int deg, const int idx, const int M, const float3 mean, const float3 campos,
+                                      const float dcol0, const float dcol1, const float dcol2, const int flags,
+                                      const float *__restrict__ shs, float *__restrict__ dL_dsh) {
+    float3 dmean = make_float3(0.f, 0.f, 0.f);
+    const float dcol[3] = {dcol0, dcol1, dcol2};
+    const float s_m32 = campos.x, s_m33 = campos.y, s_m34 = campos.z;
+    {
+        float dRGB[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) dRGB[ch] = (flags >> ch) & 1 ? 0.f : dcol[ch];
+        float sh[48];
+        load_sh(shs, idx, M, sh_ncoef(deg), sh);
+        const float3 d0 = make_float3(mean.x - s_m32, mean.y - s_m33, mean.z - s_m34);
+        const float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
+        const float x = d0.x / len, y = d0.y / len, z = d0.z / len;
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        float w[16];  // dRGB/dsh_k, identical for the three channels
+        w[0] = SH_C0;
+        w[1] = -SH_C1 * y; w[2] = SH_C1 * z; w[3] = -SH_C1 * x;
+        w[4] = SH_C2_0 * xy; w[5] = SH_C2_1 * yz; w[6] = SH_C2_2 * (2.f * zz - xx - yy); w[7] = SH_C2_3 * xz; w[8] = SH_C2_4 * (xx - yy);
+        w[9] = SH_C3_0 * y * (3.f * xx - yy); w[10] = SH_C3_1 * xy * z; w[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
+        w[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); w[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
+        w[14] = SH_C3_5 * z * (xx - yy); w[15] = SH_C3_6 * x * (xx - 3.f * yy);
+        const int nc = sh_ncoef(deg);
+        // dL/dsh[k][ch] = w[k] * dRGB[ch] for k < (deg+1)^2, zero above; constant indices only (keeps w[] in registers)
+        if (M == 16) {
+            float4 *o4 = reinterpret_cast<float4 *>(dL_dsh + (size_t)idx * 48);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                float e[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int k = (4 * i + t) / 3, ch = (4 * i + t) % 3;
+                    e[t] = (k < nc) ? w[k] * dRGB[ch] : 0.f;
+                }
+                o4[i] = make_float4(e[0], e[1], e[2], e[3]);
+            }
+        } else {
+            float *o1 = dL_dsh + (size_t)idx * 3 * M;
+#pragma unroll
+            for (int e = 0; e < 48; e++)
+                if (e < 3 * M) o1[e] = (e / 3 < nc) ? w[e / 3] * dRGB[e % 3] : 0.f;
+        }
+        float3 ddir = make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+#define S(k) sh[(k) * 3 + ch]
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            if (deg > 0) {
+                rx = -SH_C1 * S(3); ry = -SH_C1 * S(1); rz = SH_C1 * S(2);
+                if (deg > 1) {
+                    rx += SH_C2_0 * y * S(4) + SH_C2_2 * 2.f * -x * S(6) + SH_C2_3 * z * S(7) + SH_C2_4 * 2.f * x * S(8);
+                    ry += SH_C2_0 * x * S(4) + SH_C2_1 * z * S(5) + SH_C2_2 * 2.f * -y * S(6) + SH_C2_4 * 2.f * -y * S(8);
+                    rz += SH_C2_1 * y * S(5) + SH_C2_2 * 2.f * 2.f * z * S(6) + SH_C2_3 * x * S(7);
+                    if (deg > 2) {
+                        rx += SH_C3_0 * S(9) * 3.f * 2.f * xy + SH_C3_1 * S(10) * yz + SH_C3_2 * S(11) * -2.f * xy +
+                              SH_C3_3 * S(12) * -3.f * 2.f * xz + SH_C3_4 * S(13) * (-3.f * xx + 4.f * zz - yy) +
+                              SH_C3_5 * S(14) * 2.f * xz + SH_C3_6 * S(15) * 3.f * (xx - yy);
+                        ry += SH_C3_0 * S(9) * 3.f * (xx - yy) + SH_C3_1 * S(10) * xz + SH_C3_2 * S(11) * (-3.f * yy + 4.f * zz - xx) +
+                              SH_C3_3 * S(12) * -3.f * 2.f * yz + SH_C3_4 * S(13) * -2.f * xy + SH_C3_5 * S(14) * -2.f * yz +
+                              SH_C3_6 * S(15) * -3.f * 2.f * xy;
+                        rz += SH_C3_1 * S(10) * xy + SH_C3_2 * S(11) * 4.f * 2.f * yz + SH_C3_3 * S(12) * 3.f * (2.f * zz - xx - yy) +
+                              SH_C3_4 * S(13) * 4.f * 2.f * xz + SH_C3_5 * S(14) * (xx - yy);
+                    }
+                }
+            }
+#undef S
+            ddir.x += rx * dRGB[ch]; ddir.y += ry * dRGB[ch]; ddir.z += rz * dRGB[ch];
+        }
+        // dnormvdv, auxiliary.h:107-118
+        const float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
+        const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+        dmean.x += ((+sum2 - d0.x * d0.x) * ddir.x - d0.y * d0.x * ddir.y - d0.z * d0.x * ddir.z) * inv32;
+        dmean.y += (-d0.x * d0.y * ddir.x + (sum2 - d0.y * d0.y) * ddir.y - d0.z * d0.y * ddir.z) * inv32;
+        dmean.z += (-d0.x * d0.z * ddir.x - d0.y * d0.z * ddir.y + (sum2 - d0.z * d0.z) * ddir.z) * inv32;
+    
+    }
+    return dmean;
 }
 
 __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx, const int M, const float *s_m,
@@ -366,6 +450,11 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
     float4 drot = rd;                              // depth path
 
     const float3 mean = make_float3(means[i3], means[i3 + 1], means[i3 + 2]);
+    if (has_sh) {
+        const float3 dsh_mean = bwd_sh(vp.sh_degree, idx, M, mean, make_float3(s_m[32], s_m[33], s_m[34]), dcol[0], dcol[1], dcol[2],
+                                       __float_as_int(g.rgb_flags[idx].w), shs, dL_dsh);
+        dmean.x += dsh_mean.x; dmean.y += dsh_mean.y; dmean.z += dsh_mean.z;
+    }
     float3 sc = make_float3(0.f, 0.f, 0.f);
     float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
     float R[3][3];
@@ -431,72 +520,7 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
         dmean.z += (pj[8] * mw - pj[11] * mul1) * g2x + (pj[9] * mw - pj[11] * mul2) * g2y;
     }
 
-    // ---- SH path, backward.cu:152-268
-    if (has_sh) {
-        const int deg = vp.sh_degree;
-        const int flags = __float_as_int(g.rgb_flags[idx].w);
-        float dRGB[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) dRGB[ch] = (flags >> ch) & 1 ? 0.f : dcol[ch];
-        float sh[48];
-        load_sh(shs, idx, M, sh_ncoef(deg), sh);
-        const float3 d0 = make_float3(mean.x - s_m[32], mean.y - s_m[33], mean.z - s_m[34]);
-        const float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
-        const float x = d0.x / len, y = d0.y / len, z = d0.z / len;
-        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        float w[16];  // dRGB/dsh_k, identical for the three channels
-        w[0] = SH_C0;
-        w[1] = -SH_C1 * y; w[2] = SH_C1 * z; w[3] = -SH_C1 * x;
-        w[4] = SH_C2_0 * xy; w[5] = SH_C2_1 * yz; w[6] = SH_C2_2 * (2.f * zz - xx - yy); w[7] = SH_C2_3 * xz; w[8] = SH_C2_4 * (xx - yy);
-        w[9] = SH_C3_0 * y * (3.f * xx - yy); w[10] = SH_C3_1 * xy * z; w[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
-        w[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); w[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
-        w[14] = SH_C3_5 * z * (xx - yy); w[15] = SH_C3_6 * x * (xx - 3.f * yy);
-        const int nc = sh_ncoef(deg);
-        float out[48];
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) out[3 * k + ch] = (k < nc) ? w[k] * dRGB[ch] : 0.f;
-        if (M == 16) {
-            float4 *o = reinterpret_cast<float4 *>(dL_dsh + (size_t)idx * 48);
-#pragma unroll
-            for (int i = 0; i < 12; i++) o[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
-        } else {
-            for (int i = 0; i < 3 * M; i++) dL_dsh[(size_t)idx * 3 * M + i] = (i < 48) ? out[i] : 0.f;
-        }
-        float3 ddir = make_float3(0.f, 0.f, 0.f);
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-#define S(k) sh[(k) * 3 + ch]
-            float rx = 0.f, ry = 0.f, rz = 0.f;
-            if (deg > 0) {
-                rx = -SH_C1 * S(3); ry = -SH_C1 * S(1); rz = SH_C1 * S(2);
-                if (deg > 1) {
-                    rx += SH_C2_0 * y * S(4) + SH_C2_2 * 2.f * -x * S(6) + SH_C2_3 * z * S(7) + SH_C2_4 * 2.f * x * S(8);
-                    ry += SH_C2_0 * x * S(4) + SH_C2_1 * z * S(5) + SH_C2_2 * 2.f * -y * S(6) + SH_C2_4 * 2.f * -y * S(8);
-                    rz += SH_C2_1 * y * S(5) + SH_C2_2 * 2.f * 2.f * z * S(6) + SH_C2_3 * x * S(7);
-                    if (deg > 2) {
-                        rx += SH_C3_0 * S(9) * 3.f * 2.f * xy + SH_C3_1 * S(10) * yz + SH_C3_2 * S(11) * -2.f * xy +
-                              SH_C3_3 * S(12) * -3.f * 2.f * xz + SH_C3_4 * S(13) * (-3.f * xx + 4.f * zz - yy) +
-                              SH_C3_5 * S(14) * 2.f * xz + SH_C3_6 * S(15) * 3.f * (xx - yy);
-                        ry += SH_C3_0 * S(9) * 3.f * (xx - yy) + SH_C3_1 * S(10) * xz + SH_C3_2 * S(11) * (-3.f * yy + 4.f * zz - xx) +
-                              SH_C3_3 * S(12) * -3.f * 2.f * yz + SH_C3_4 * S(13) * -2.f * xy + SH_C3_5 * S(14) * -2.f * yz +
-                              SH_C3_6 * S(15) * -3.f * 2.f * xy;
-                        rz += SH_C3_1 * S(10) * xy + SH_C3_2 * S(11) * 4.f * 2.f * yz + SH_C3_3 * S(12) * 3.f * (2.f * zz - xx - yy) +
-                              SH_C3_4 * S(13) * 4.f * 2.f * xz + SH_C3_5 * S(14) * (xx - yy);
-                    }
-                }
-            }
-#undef S
-            ddir.x += rx * dRGB[ch]; ddir.y += ry * dRGB[ch]; ddir.z += rz * dRGB[ch];
-        }
-        // dnormvdv, auxiliary.h:107-118
-        const float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
-        const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-        dmean.x += ((+sum2 - d0.x * d0.x) * ddir.x - d0.y * d0.x * ddir.y - d0.z * d0.x * ddir.z) * inv32;
-        dmean.y += (-d0.x * d0.y * ddir.x + (sum2 - d0.y * d0.y) * ddir.y - d0.z * d0.y * ddir.z) * inv32;
-        dmean.z += (-d0.x * d0.z * ddir.x - d0.y * d0.z * ddir.y + (sum2 - d0.z * d0.z) * ddir.z) * inv32;
-    }
+    // (SH path: bwd_sh, run first)
 
     // ---- cov3D -> scale, quaternion, backward.cu:426-487
     if (has_sr) {
@@ -542,7 +566,7 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
 // Two duties per CTA: (1) zero the gradients of the culled Gaussians of its own index range (light, streaming);
 // (2) run the full backward for one slice of the compact visible list built by the forward preprocess, so that the
 // register-heavy path executes with full warps instead of ~40 % of the lanes.
-__global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
+__global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
                                                                 const float *__restrict__ means, const float *__restrict__ scales,
                                                                 const float *__restrict__ rots, const float *__restrict__ shs,
                                                                 const float *__restrict__ cov3D_precomp, const int *__restrict__ radii,
@@ -554,7 +578,22 @@ __global__ void __launch_bounds__(256, 2) preprocess_bwd_kernel(const ViewParams
     else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < P && !(radii[idx] > 0)) bwd_zero(idx, M, shs != nullptr, cov3D_precomp == nullptr, o);
+    const bool culled = idx < P && !(radii[idx] > 0);
+    const bool coop_sh = (shs != nullptr) && (M == 16);
+    if (coop_sh) {
+        // the warp's 32 dL_dsh rows are one contiguous 6 KB block: zero the culled rows with fully coalesced stores
+        const uint32_t cm = __ballot_sync(0xffffffffu, culled);
+        if (cm) {
+            const int lane = threadIdx.x & 31;
+            float4 *blk = reinterpret_cast<float4 *>(o.dL_dsh + (size_t)(idx - lane) * 48);
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                const int f = lane + 32 * k, row = f / 12;
+                if ((cm >> row) & 1u) blk[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    if (culled) bwd_zero(idx, M, shs != nullptr, cov3D_precomp == nullptr, o, coop_sh);
     const uint32_t V = *vis_count;
     if ((uint32_t)idx < V) bwd_visible(vp, (int)g.vis_list[idx], M, s_m, means, scales, rots, shs, cov3D_precomp, g, rec, o);
 }
