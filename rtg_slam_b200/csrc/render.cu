@@ -269,139 +269,12 @@ __device__ __forceinline__ int reduce9_slot(const int lane) {
     return cnt > 0 ? base : -1;
 }
 
-__global__ void __launch_bounds__(256, 4) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b, const ImgState img,
-                                                         const int *__restrict__ counters, const float *__restrict__ means,
-                                                         const float *__restrict__ scales, const float *__restrict__ rots,
-                                                         const float *__restrict__ final_T, const int *__restrict__ hit_image,
-                                                         const float *__restrict__ dL_dcolor, const float *__restrict__ dL_ddepth,
-                                                         float *__restrict__ rec) {
-    __shared__ float4 s_s0[BATCH];
-    __shared__ float4 s_s1[BATCH];
-    __shared__ float4 s_rgb[BATCH];
-    __shared__ int s_id[BATCH];
-    __shared__ uint32_t s_mask[BATCH];
-    __shared__ uint32_t s_max[8];
-
-    if (counters[2]) return;
-    if ((int)blockIdx.x >= counters[1]) return;  // empty tiles sit at the end of the launch order
-    const int tile = (int)b.active[blockIdx.x];
-    const uint32_t start = b.tile_offset[tile];
-    const int n = (int)(b.tile_offset[tile + 1] - start);
-    if (n == 0) return;
-    int px, py;
-    bool inside;
-    pixel_of(vp, tile, px, py, inside);
-    const int pix_id = vp.W * py + px;
-    const int N = vp.H * vp.W;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const float2 pixf = make_float2((float)px, (float)py);
-    const float tx0 = (float)((tile % vp.tiles_x) * RTG_TILE), ty0 = (float)((tile / vp.tiles_x) * RTG_TILE);
-    const uint32_t a_s0 = smem_addr(s_s0), a_s1 = smem_addr(s_s1), a_rgb = smem_addr(s_rgb), a_id = smem_addr(s_id),
-                   a_mask = smem_addr(s_mask);
-
-    const float T_final = inside ? final_T[pix_id] : 0.f;
-    float T = T_final;
-    const uint32_t last_contributor = inside ? img.n_contrib[pix_id] : 0u;
-    float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
-    if (inside) {
-        dLp0 = dL_dcolor[pix_id]; dLp1 = dL_dcolor[N + pix_id]; dLp2 = dL_dcolor[2 * N + pix_id];
-    }
-    const float bg0 = __ldg(vp.bg), bg1 = __ldg(vp.bg + 1), bg2 = __ldg(vp.bg + 2);
-    const float bg_dot_dpixel = bg0 * dLp0 + bg1 * dLp1 + bg2 * dLp2;
-
-    // only the first `m` entries of the list were blended by some pixel of this tile
-    uint32_t wmax = last_contributor;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, o));
-    if (lane == 0) s_max[w] = wmax;
-    __syncthreads();
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) m = max(m, s_max[k]);
-
-    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
-    const int my_slot = (lane & 1) ? -1 : reduce9_slot(lane);  // lanes 2k and 2k+1 hold the same total: one of them adds it
-    const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
-
-    const int rounds = ((int)m + BATCH - 1) / BATCH;
-    for (int i = 0; i < rounds; i++) {
-        __syncthreads();
-        const int progress = i * BATCH + threadIdx.x;  // position from the back of the prefix
-        if (progress < (int)m) {
-            const int id = (int)b.point_list[start + (m - 1 - progress)];
-            const float4 s0 = __ldg(g.splat + 2 * (size_t)id), s1 = __ldg(g.splat + 2 * (size_t)id + 1);
-            s_id[threadIdx.x] = id;
-            s_s0[threadIdx.x] = s0;
-            s_s1[threadIdx.x] = s1;
-            s_rgb[threadIdx.x] = __ldg(g.rgb_flags + id);
-            s_mask[threadIdx.x] = patch_mask(s0, s1, tx0, ty0);
-        }
-        __syncthreads();
-        const int cnt = min(BATCH, (int)m - i * BATCH);
-        const int chunks = (cnt + 31) >> 5;
-        for (int c = 0; c < chunks; c++) {
-            const int e = (c << 5) + lane;
-            // list position of staged entry e (== the reference's `contributor`); entries at or beyond the warp's
-            // deepest blended position are skipped by every lane
-            const uint32_t pos_e = m - 1 - (uint32_t)(i * BATCH + e);
-            const uint32_t mm = (e < cnt && pos_e < wmax) ? lds32(a_mask + e * 4) : 0u;
-            uint32_t bits = __ballot_sync(FULL, (mm >> w) & 1u);
-            while (bits) {
-                const int j = (c << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const uint32_t pos = m - 1 - (uint32_t)(i * BATCH + j);
-                float v[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) v[k] = 0.f;
-                bool active = pos < last_contributor;
-                if (active) {
-                    const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
-                    const float dx = s0.x - pixf.x, dy = s0.y - pixf.y;
-                    const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
-                    active = (power <= 0.0f) && (power >= -s0.z);
-                    if (active) {
-                        const float G = expf(power);
-                        const float alpha = fminf(0.99f, s1.w * G);
-                        active = !(alpha < 1.0f / 255.0f);
-                        if (active) {
-                            const float inv_1ma = __frcp_rn(1.f - alpha);
-                            T = T * inv_1ma;
-                            const float dch = alpha * T;
-                            const float4 col = lds128(a_rgb + j * 16);
-                            accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0; lc0 = col.x;
-                            accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1; lc1 = col.y;
-                            accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2; lc2 = col.z;
-                            float dL_dalpha = (col.x - accum0) * dLp0;
-                            dL_dalpha += (col.y - accum1) * dLp1;
-                            dL_dalpha += (col.z - accum2) * dLp2;
-                            v[REC_COLOR + 0] = dch * dLp0;
-                            v[REC_COLOR + 1] = dch * dLp1;
-                            v[REC_COLOR + 2] = dch * dLp2;
-                            dL_dalpha *= T;
-                            last_alpha = alpha;
-                            if (bg_dot_dpixel != 0.f) dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
-                            const float dL_dG = s1.w * dL_dalpha;
-                            const float gdx = G * dx, gdy = G * dy;
-                            const float dG_ddelx = -gdx * s1.x - gdy * s1.y;
-                            const float dG_ddely = -gdy * s1.z - gdx * s1.y;
-                            v[REC_MEAN2D + 0] = dL_dG * dG_ddelx * ddelx_dx;
-                            v[REC_MEAN2D + 1] = dL_dG * dG_ddely * ddely_dy;
-                            v[REC_CONIC + 0] = -0.5f * gdx * dx * dL_dG;
-                            v[REC_CONIC + 1] = -0.5f * gdx * dy * dL_dG;
-                            v[REC_CONIC + 2] = -0.5f * gdy * dy * dL_dG;
-                            v[REC_OPACITY] = G * dL_dalpha;
-                        }
-                    }
-                }
-                if (!__any_sync(FULL, active)) continue;
-                const float tot = warp_reduce9(v, lane);
-                if (my_slot >= 0) atomicAdd(rec + (size_t)lds32(a_id + j * 4) * RTG_REC + my_slot, tot);
-            }
-        }
-    }
-
-    // depth-hit gradient (backward.cu:997-1065)
+// Depth-hit gradient of one pixel (backward.cu:997-1065): the first opaque Gaussian of the pixel receives the gradient
+// of the rendered depth w.r.t. its centre and, on the plane branch, w.r.t. its quaternion (through the surfel normal).
+__device__ __forceinline__ void depth_hit_grad(const ViewParams &vp, const GeomState &g, const float *__restrict__ scales,
+                                               const float *__restrict__ rots, const int *__restrict__ hit_image,
+                                               const float *__restrict__ dL_ddepth, float *__restrict__ rec, const int px,
+                                               const int py, const int pix_id, const bool inside) {
     if (inside) {
         const int gid = hit_image[pix_id];
         if (gid >= 0) {
@@ -470,6 +343,165 @@ __global__ void __launch_bounds__(256, 4) render_bwd_kernel(const ViewParams vp,
     }
 }
 
+// Per-pixel replay state of the backward (one pixel): everything the reference keeps in registers between entries.
+struct BwdPix {
+    float T, T_final, accum0, accum1, accum2, last_alpha, lc0, lc1, lc2, dLp0, dLp1, dLp2, bg_dot, pyf;
+    uint32_t last_contributor;
+};
+
+// One (pixel, Gaussian) pair of the back-to-front replay (backward.cu:926-995); adds the 9 gradient terms to v[].
+__device__ __forceinline__ bool bwd_pair(BwdPix &p, const uint32_t pos, const float4 s0, const float4 s1, const float dx,
+                                         const uint32_t a_rgb_j, const float ddelx_dx, const float ddely_dy, float v[9]) {
+    if (!(pos < p.last_contributor)) return false;
+    const float dy = s0.y - p.pyf;
+    const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
+    if (!((power <= 0.0f) && (power >= -s0.z))) return false;  // skipped by the reference / certainly below 1/255
+    const float G = expf(power);
+    const float alpha = fminf(0.99f, s1.w * G);
+    if (alpha < 1.0f / 255.0f) return false;
+    const float inv_1ma = __frcp_rn(1.f - alpha);
+    p.T = p.T * inv_1ma;
+    const float dch = alpha * p.T;
+    const float4 col = lds128(a_rgb_j);
+    p.accum0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.accum0; p.lc0 = col.x;
+    p.accum1 = p.last_alpha * p.lc1 + (1.f - p.last_alpha) * p.accum1; p.lc1 = col.y;
+    p.accum2 = p.last_alpha * p.lc2 + (1.f - p.last_alpha) * p.accum2; p.lc2 = col.z;
+    float dL_dalpha = (col.x - p.accum0) * p.dLp0;
+    dL_dalpha += (col.y - p.accum1) * p.dLp1;
+    dL_dalpha += (col.z - p.accum2) * p.dLp2;
+    v[REC_COLOR + 0] += dch * p.dLp0;
+    v[REC_COLOR + 1] += dch * p.dLp1;
+    v[REC_COLOR + 2] += dch * p.dLp2;
+    dL_dalpha *= p.T;
+    p.last_alpha = alpha;
+    if (p.bg_dot != 0.f) dL_dalpha += (-p.T_final * inv_1ma) * p.bg_dot;
+    const float dL_dG = s1.w * dL_dalpha;
+    const float gdx = G * dx, gdy = G * dy;
+    const float dG_ddelx = -gdx * s1.x - gdy * s1.y;
+    const float dG_ddely = -gdy * s1.z - gdx * s1.y;
+    v[REC_MEAN2D + 0] += dL_dG * dG_ddelx * ddelx_dx;
+    v[REC_MEAN2D + 1] += dL_dG * dG_ddely * ddely_dy;
+    v[REC_CONIC + 0] += -0.5f * gdx * dx * dL_dG;
+    v[REC_CONIC + 1] += -0.5f * gdx * dy * dL_dG;
+    v[REC_CONIC + 2] += -0.5f * gdy * dy * dL_dG;
+    v[REC_OPACITY] += G * dL_dalpha;
+    return true;
+}
+
+// Backward compositing. 128 threads per tile; a warp owns an 8x8 pixel patch and every lane two vertically adjacent
+// pixels, so the per-entry costs that do not depend on the pixel (list walk, shared-memory fetch of the splat, the
+// warp reduction and the atomic) are paid once per 64 pixels.
+#define BWD_THREADS 128
+__global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b,
+                                                               const ImgState img, const int *__restrict__ counters,
+                                                               const float *__restrict__ means, const float *__restrict__ scales,
+                                                               const float *__restrict__ rots, const float *__restrict__ final_T,
+                                                               const int *__restrict__ hit_image, const float *__restrict__ dL_dcolor,
+                                                               const float *__restrict__ dL_ddepth, float *__restrict__ rec) {
+    __shared__ float4 s_s0[BATCH];
+    __shared__ float4 s_s1[BATCH];
+    __shared__ float4 s_rgb[BATCH];
+    __shared__ int s_id[BATCH];
+    __shared__ uint32_t s_mask[BATCH];
+    __shared__ uint32_t s_max[4];
+
+    if (counters[2]) return;
+    if ((int)blockIdx.x >= counters[1]) return;  // empty tiles sit at the end of the launch order
+    const int tile = (int)b.active[blockIdx.x];
+    const uint32_t start = b.tile_offset[tile];
+    const int n = (int)(b.tile_offset[tile + 1] - start);
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
+    // warp w: patch (w & 1, w >> 1) of 8x8 pixels; lane: column lane & 7, rows 2*(lane >> 3) and 2*(lane >> 3) + 1
+    const int px = tx * RTG_TILE + (w & 1) * 8 + (lane & 7);
+    const int pyA = ty * RTG_TILE + (w >> 1) * 8 + 2 * (lane >> 3), pyB = pyA + 1;
+    const bool insA = px < vp.W && pyA < vp.H, insB = px < vp.W && pyB < vp.H;
+    const int pidA = vp.W * pyA + px, pidB = vp.W * pyB + px;
+    const int N = vp.H * vp.W;
+    const float pxf = (float)px;
+    const float tx0 = (float)(tx * RTG_TILE), ty0 = (float)(ty * RTG_TILE);
+    const uint32_t a_s0 = smem_addr(s_s0), a_s1 = smem_addr(s_s1), a_rgb = smem_addr(s_rgb), a_id = smem_addr(s_id),
+                   a_mask = smem_addr(s_mask);
+    const float bg0 = __ldg(vp.bg), bg1 = __ldg(vp.bg + 1), bg2 = __ldg(vp.bg + 2);
+
+    BwdPix A, B;
+    {
+        A.T_final = insA ? final_T[pidA] : 0.f; B.T_final = insB ? final_T[pidB] : 0.f;
+        A.T = A.T_final; B.T = B.T_final;
+        A.last_contributor = insA ? img.n_contrib[pidA] : 0u; B.last_contributor = insB ? img.n_contrib[pidB] : 0u;
+        A.dLp0 = insA ? dL_dcolor[pidA] : 0.f; A.dLp1 = insA ? dL_dcolor[N + pidA] : 0.f; A.dLp2 = insA ? dL_dcolor[2 * N + pidA] : 0.f;
+        B.dLp0 = insB ? dL_dcolor[pidB] : 0.f; B.dLp1 = insB ? dL_dcolor[N + pidB] : 0.f; B.dLp2 = insB ? dL_dcolor[2 * N + pidB] : 0.f;
+        A.bg_dot = bg0 * A.dLp0 + bg1 * A.dLp1 + bg2 * A.dLp2; B.bg_dot = bg0 * B.dLp0 + bg1 * B.dLp1 + bg2 * B.dLp2;
+        A.accum0 = A.accum1 = A.accum2 = A.last_alpha = A.lc0 = A.lc1 = A.lc2 = 0.f;
+        B.accum0 = B.accum1 = B.accum2 = B.last_alpha = B.lc0 = B.lc1 = B.lc2 = 0.f;
+        A.pyf = (float)pyA; B.pyf = (float)pyB;
+    }
+
+    // only the first `m` entries of the list were blended by some pixel of this tile
+    uint32_t wmax = max(A.last_contributor, B.last_contributor);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, o));
+    if (lane == 0) s_max[w] = wmax;
+    __syncthreads();
+    const uint32_t m = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
+
+    const int my_slot = (lane & 1) ? -1 : reduce9_slot(lane);  // lanes 2k and 2k+1 hold the same total: one of them adds it
+    const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
+
+    const int rounds = ((int)m + BATCH - 1) / BATCH;
+    for (int i = 0; i < rounds; i++) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < BATCH; q += BWD_THREADS) {
+            const int progress = i * BATCH + q;  // position from the back of the prefix
+            if (progress < (int)m) {
+                const int id = (int)b.point_list[start + (m - 1 - progress)];
+                const float4 s0 = __ldg(g.splat + 2 * (size_t)id), s1 = __ldg(g.splat + 2 * (size_t)id + 1);
+                s_id[q] = id;
+                s_s0[q] = s0;
+                s_s1[q] = s1;
+                s_rgb[q] = __ldg(g.rgb_flags + id);
+                uint32_t mk = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float x0 = tx0 + (float)((k & 1) * 8), y0 = ty0 + (float)((k >> 1) * 8);
+                    if (!rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, x0, x0 + 7.f, y0, y0 + 7.f)) mk |= (1u << k);
+                }
+                s_mask[q] = mk;
+            }
+        }
+        __syncthreads();
+        const int cnt = min(BATCH, (int)m - i * BATCH);
+        const int chunks = (cnt + 31) >> 5;
+        for (int c = 0; c < chunks; c++) {
+            const int e = (c << 5) + lane;
+            // list position of staged entry e (== the reference's `contributor`); entries at or beyond the warp's
+            // deepest blended position are skipped by every lane
+            const uint32_t pos_e = m - 1 - (uint32_t)(i * BATCH + e);
+            const uint32_t mm = (e < cnt && pos_e < wmax) ? lds32(a_mask + e * 4) : 0u;
+            uint32_t bits = __ballot_sync(FULL, (mm >> w) & 1u);
+            while (bits) {
+                const int j = (c << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t pos = m - 1 - (uint32_t)(i * BATCH + j);
+                float v[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) v[k] = 0.f;
+                const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
+                const float dx = s0.x - pxf;
+                const bool actA = bwd_pair(A, pos, s0, s1, dx, a_rgb + j * 16, ddelx_dx, ddely_dy, v);
+                const bool actB = bwd_pair(B, pos, s0, s1, dx, a_rgb + j * 16, ddelx_dx, ddely_dy, v);
+                if (!__any_sync(FULL, actA || actB)) continue;
+                const float tot = warp_reduce9(v, lane);
+                if (my_slot >= 0) atomicAdd(rec + (size_t)lds32(a_id + j * 4) * RTG_REC + my_slot, tot);
+            }
+        }
+    }
+
+    depth_hit_grad(vp, g, scales, rots, hit_image, dL_ddepth, rec, px, pyA, pidA, insA);
+    depth_hit_grad(vp, g, scales, rots, hit_image, dL_ddepth, rec, px, pyB, pidB, insB);
+}
+
 void launch_render_fwd(const ViewParams &vp, const GeomState &g, const BinState &b, const ImgState &img, const int32_t *counters,
                        float *out_color, float *out_depth, int *out_hit_color, int *out_hit_depth, float *out_hcw,
                        float *out_hdw, float *out_T, cudaStream_t s) {
@@ -484,7 +516,7 @@ void launch_render_bwd(const ViewParams &vp, const GeomState &g, const BinState 
                        const float *dL_dcolor, const float *dL_ddepth, float *rec, cudaStream_t s) {
     const int T = vp.tiles_x * vp.tiles_y;
     ProfScope ps(K_RENDER_BWD, s);
-    render_bwd_kernel<<<T, 256, 0, s>>>(vp, g, b, img, counters, means, scales, rots, final_T, hit_image, dL_dcolor, dL_ddepth, rec);
+    render_bwd_kernel<<<T, BWD_THREADS, 0, s>>>(vp, g, b, img, counters, means, scales, rots, final_T, hit_image, dL_dcolor, dL_ddepth, rec);
 }
 
 }  // namespace rtg
