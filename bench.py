@@ -371,23 +371,22 @@ def rast_counters(dev):
 
 
 def cpu_baseline(args, cam):
-    """The reference algorithm on the host cores (oracle port), one bounded sample of the same workload."""
+    """The reference algorithm on the host cores (oracle port): one full frame of the same workload, fwd+bwd."""
     from oracle.splat_oracle import OracleRender
     from rtg_slam_b200 import scene
     cores = os.cpu_count() or 1
     g = scene.surfel_room(args.gaussians, seed=2024)
     gc, gd = scene.upstream_grads(cam, seed=5)
-    th, tw = cam.tile_grid
-    rng = np.random.default_rng(0)
-    frac = 0.25
-    mask = (rng.uniform(size=(th, tw)) < frac).astype(np.int32)
-    t0 = time.perf_counter()
-    o = OracleRender(cam, g, tile_mask=mask, precision="f32", nthreads=cores)
-    o.backward(gc, gd, nthreads=cores)
-    o.close()
-    dt = time.perf_counter() - t0
-    return {"value": float(mask.mean()) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"one frame restricted to {mask.mean():.2f} of the tiles (random tile mask), fwd+bwd, scaled to a full frame; oracle/splat_oracle.c with OpenMP"}
+    best = None
+    for _ in range(2):  # first pass warms the page cache / OpenMP pool
+        t0 = time.perf_counter()
+        o = OracleRender(cam, g, precision="f32", nthreads=cores)
+        o.backward(gc, gd, nthreads=cores)
+        o.close()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": 1.0 / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "one full frame (all tiles), fwd+bwd, best of 2; oracle/splat_oracle.c with OpenMP (the reference has no CPU render path)"}
 
 
 def extras(dev, cam, t, leaves, step):

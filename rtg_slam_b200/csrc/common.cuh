@@ -210,7 +210,12 @@ __device__ __forceinline__ int pair_owner(const uint32_t *excl, uint32_t k) {
 }
 
 // explicit shared-state-space accesses with a precomputed 32-bit base (keeps address arithmetic out of the loops)
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    // opaque to the optimiser: otherwise ptxas re-materialises the address (S2R SR_CgaCtaId + LEA chain) at every use
+    asm volatile("" : "+r"(a));
+    return a;
+}
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");

@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                         }
                     }
                 }
-                if (__all_sync(FULL, done)) { bits = 0u; c = chunks; }
             }
+            if (__all_sync(FULL, done)) break;  // checked once per 32 entries: a finished warp skips visits cheaply
         }
     }
 
