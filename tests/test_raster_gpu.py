@@ -105,6 +105,22 @@ def test_oversized_tile_lists(cuda_device, P):
     assert longest > (2 * 4096 if P < 50_000 else 4 * 8192), longest  # ours are shorter (exact culling), still past the limits
 
 
+def test_equal_depth_ties_follow_gaussian_index(cuda_device):
+    """Splats with bit-identical view depth composite in ascending Gaussian index order (the reference's radix sort is
+    stable and duplicateWithKeys emits in index order, SURVEY appendix #9)."""
+    cam = scene.make_camera("small")
+    g0 = scene.random_blobs(1200, seed=31)
+    rng = np.random.default_rng(3)
+    g = {}
+    for k, v in g0.items():  # every Gaussian three times, same centre (=> same depth), different colour / opacity
+        g[k] = np.ascontiguousarray(np.concatenate([v, v, v]))
+    g["shs"][1200:, 0] = rng.uniform(-1.5, 1.5, (2400, 3)).astype(np.float32)
+    g["opacity"][2400:] = rng.uniform(0.05, 0.9, (1200, 1)).astype(np.float32)
+    perm = rng.permutation(3600)
+    g = {k: np.ascontiguousarray(v[perm]) for k, v in g.items()}
+    check_against_oracle(cam, g, cuda_device, label="ties")
+
+
 def test_edge_cases(cuda_device):
     from rtg_slam_b200.rasterizer import GaussianRasterizer
     dev = cuda_device
