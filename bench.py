@@ -151,6 +151,7 @@ def main():
     from rtg_slam_b200 import _lib, scene
     from rtg_slam_b200.rasterizer import GaussianRasterizer, GaussianRasterizationSettings
     from rtg_slam_b200.render import Renderer
+    from rtg_slam_b200.loss import l1_color_depth_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -282,10 +283,8 @@ def main():
         cur.wait_event(uploaded[k])
         fd = frame_dev[k]
         out = renderer.render(vcs[k], data)
-        color_loss = (out["render"] - fd[:3]).abs().mean()                  # l1_loss, utils/loss_utils.py:27
-        valid = ((out["depth_index_map"] != -1) & (fd[3:4] > 0)).float()
-        depth_loss = ((out["depth"] - fd[3:4]).abs() * valid).sum() / valid.sum().clamp_min(1.0)
-        loss = 0.8 * color_loss + 1.0 * depth_loss                          # configs/base.yaml:76-77 weights
+        # colour L1 + depth L1 of Mapping.loss_update (mapper.py:402-431), weights of configs/base.yaml:76-77
+        loss, _parts = l1_color_depth_loss(out, fd[:3], fd[3], color_weight=0.8, depth_weight=1.0, depth_error_max=0.1)
         loss.backward()
         consumed[k].record(cur)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=False)       # the loss.item() of mapper.py:459

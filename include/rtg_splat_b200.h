@@ -147,6 +147,25 @@ int rtg_icp_fill_model_depth(float *render_depth, const float *frame_depth, cons
                              const float *frame_normal, int32_t H, int32_t W, float distance_threshold,
                              float normal_threshold, void *stream);
 
+/* ---- image-space glue between the rasterizer forward and backward -------------
+ * Fused masked L1 colour + depth loss of Mapping.loss_update (SLAM/multiprocess/mapper.py:402-431,444-451, with
+ * l1_loss of utils/loss_utils.py:27-31) and its gradients w.r.t. the rendered colour and depth:
+ *   colour = mean |render - gt_color| over the render_mask pixels (NULL = all) x 3 channels,
+ *   depth  = mean |depth - gt_depth| over pixels with depth_index != -1, gt_depth > 0, depth - gt_depth <
+ *            depth_error_max and the render mask,  loss = color_weight*colour + depth_weight*depth.
+ * render (3,H,W), depth (1,H,W), depth_index (1,H,W) are rasterizer outputs; gt_color is (H,W,3) if
+ * gt_channels_last else (3,H,W); gt_depth (H,W); render_mask (H,W) bytes. loss_out: 4 device floats
+ * {loss, colour, depth, n_depth}. An empty selection contributes 0 (torch's mean of an empty tensor is NaN).
+ * ws: rtg_loss_workspace_bytes() bytes. */
+size_t rtg_loss_workspace_bytes(void);
+int rtg_loss_l1(const float *render, const float *depth, const int32_t *depth_index, const float *gt_color, const float *gt_depth,
+                const uint8_t *render_mask, int32_t H, int32_t W, int32_t gt_channels_last, float color_weight, float depth_weight,
+                float depth_error_max, float *dL_dcolor, float *dL_ddepth, float *loss_out, void *ws, void *stream);
+
+/* render_normal of Renderer.render (SLAM/render.py:130-133): out (3,H,W) = normal[depth_index] where the index is
+ * > -1, zeros elsewhere; normal is (P,3). */
+int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream);
+
 /* ---- measurement hook (no reference counterpart) ---------------------------------------------
  * When enabled, every kernel launch of this library is bracketed by CUDA events on its launching stream.
  * rtg_profile_read synchronises the device and returns, per kernel id, the summed duration (ms) and the number

@@ -21,6 +21,11 @@ void launch_icp_solve_level(const float *v0, const float *n0, const float *v1, c
                             float *valid_ratio, void *ws, cudaStream_t s);
 void launch_icp_p2p(const float *v_t0, const float *v_t1, const float *n_t0, int H, int W, const float *pose, float *loss,
                     void *ws, cudaStream_t s);
+size_t loss_ws_bytes();
+void launch_loss_l1(const float *render, const float *depth, const int *depth_index, const float *gt_color, const float *gt_depth,
+                    const uint8_t *mask, int H, int W, int channels_last, float color_weight, float depth_weight,
+                    float depth_error_max, float *dL_dcolor, float *dL_ddepth, float *loss_out, void *ws, cudaStream_t s);
+void launch_normal_map(const float *normal, const int *depth_index, int H, int W, float *out, cudaStream_t s);
 void launch_icp_fill(float *render_depth, const float *frame_depth, const float *rn, const float *fn, int H, int W, float dthr,
                      float nthr, cudaStream_t s);
 }  // namespace rtg
@@ -272,6 +277,24 @@ int rtg_icp_fill_model_depth(float *render_depth, const float *frame_depth, cons
     rtg::launch_icp_fill(render_depth, frame_depth, render_normal, frame_normal, H, W, distance_threshold, normal_threshold,
                          reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_icp_fill_model_depth");
+}
+
+size_t rtg_loss_workspace_bytes(void) { return rtg::loss_ws_bytes(); }
+
+int rtg_loss_l1(const float *render, const float *depth, const int32_t *depth_index, const float *gt_color, const float *gt_depth,
+                const uint8_t *render_mask, int32_t H, int32_t W, int32_t gt_channels_last, float color_weight, float depth_weight,
+                float depth_error_max, float *dL_dcolor, float *dL_ddepth, float *loss_out, void *ws, void *stream) {
+    if (!render || !depth || !depth_index || !gt_color || !gt_depth || !dL_dcolor || !dL_ddepth || !loss_out || !ws || H <= 0 || W <= 0)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_loss_l1: bad arguments");
+    rtg::launch_loss_l1(render, depth, depth_index, gt_color, gt_depth, render_mask, H, W, gt_channels_last, color_weight, depth_weight,
+                        depth_error_max, dL_dcolor, dL_ddepth, loss_out, ws, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_loss_l1");
+}
+
+int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream) {
+    if (!normal || !depth_index || !out || H <= 0 || W <= 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_normal_map: bad arguments");
+    rtg::launch_normal_map(normal, depth_index, H, W, out, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_normal_map");
 }
 
 int rtg_profile_enable(int32_t on) {

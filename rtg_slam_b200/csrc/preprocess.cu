@@ -231,7 +231,7 @@ __device__ __forceinline__ bool preprocess_one(const ViewParams &vp, const int i
     return true;
 }
 
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const ViewParams vp, const int P, const int M,
+__global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(const ViewParams vp, const int P, const int M,
                                                              const float *__restrict__ means, const float *__restrict__ scales,
                                                              const float *__restrict__ rots, const float *__restrict__ opac,
                                                              const float *__restrict__ shs, const float *__restrict__ colors_precomp,

@@ -6,11 +6,14 @@ same result dictionary. The per-pixel normal map is produced without the boolean
 reference (render.py:130-133), which forces a host synchronisation (`nonzero`)."""
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import numpy as np
 import torch
 
+from . import _lib
+from ._lib import check
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 
 
@@ -70,10 +73,15 @@ class Renderer:
         )
         rendered_image, rendered_depth, color_index_map, depth_index_map, color_hit_weight, depth_hit_weight, T_map = res[:7]
 
-        # normal[depth_index_map] where the index is > -1, zeros elsewhere (render.py:130-133)
-        valid = depth_index_map[0] > -1
-        idx = depth_index_map[0].clamp_min(0).long()
-        render_normal = (normal[idx] * valid[..., None]).permute(2, 0, 1).contiguous()
+        # normal[depth_index_map] where the index is > -1, zeros elsewhere (render.py:130-133): one gather kernel
+        render_normal = torch.empty_like(rendered_image)
+        nrm = normal.detach()
+        if not nrm.is_cuda or nrm.dtype != torch.float32:
+            raise TypeError("gaussian_data['normal'] must be a CUDA float32 tensor")
+        H, W = rendered_image.shape[1:]
+        check(_lib.lib().rtg_normal_map(C.c_void_p(nrm.contiguous().data_ptr()), C.c_void_p(depth_index_map.data_ptr()), H, W,
+                                        C.c_void_p(render_normal.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream(rendered_image.device).cuda_stream)), "rtg_normal_map")
 
         return {
             "render": rendered_image,

@@ -133,3 +133,40 @@ def test_renderer_api(cuda_device):
     ref = torch.zeros_like(out["render"])
     ref[:, idx > -1] = t["normal"][idx[idx > -1].long()].permute(1, 0)  # the reference's own expression (render.py:130-133)
     assert torch.equal(ref, out["normal"])
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_fused_loss_matches_the_reference_expressions(cuda_device, use_mask):
+    """rtg_slam_b200.loss.l1_color_depth_loss against the eager expressions of Mapping.loss_update
+    (mapper.py:402-431,444-451), values and gradients through the rasterizer outputs."""
+    from rtg_slam_b200.loss import l1_color_depth_loss
+    dev = cuda_device
+    torch.manual_seed(3)
+    H, W = 75, 100
+    render = torch.rand(3, H, W, device=dev, requires_grad=True)
+    depth = (torch.rand(1, H, W, device=dev) * 3).requires_grad_(True)
+    depth_index = torch.randint(-1, 50, (1, H, W), device=dev, dtype=torch.int32)
+    gt_color = torch.rand(H, W, 3, device=dev)
+    gt_depth = torch.rand(H, W, 1, device=dev) * 3
+    gt_depth[torch.rand(H, W, 1, device=dev) < 0.1] = 0
+    gt_depth = torch.where(torch.rand(H, W, 1, device=dev) < 0.5, depth.detach().permute(1, 2, 0) + 0.05 * torch.randn(H, W, 1, device=dev), gt_depth)
+    mask = (torch.rand(H, W, device=dev) < 0.6) if use_mask else None
+    loss, parts = l1_color_depth_loss({"render": render, "depth": depth, "depth_index_map": depth_index}, gt_color, gt_depth,
+                                      render_mask=mask, color_weight=0.8, depth_weight=1.0, depth_error_max=0.1)
+    loss.backward()
+    g1, g2 = render.grad.clone(), depth.grad.clone()
+    render.grad = None; depth.grad = None
+    # the reference's expressions
+    image, d, di = render.permute(1, 2, 0), depth.permute(1, 2, 0), depth_index.permute(1, 2, 0)
+    rm = torch.ones(H, W, dtype=torch.bool, device=dev) if mask is None else mask.bool()
+    color_loss = torch.abs(image[rm] - gt_color[rm]).mean()
+    err = d - gt_depth
+    valid = (di != -1).squeeze() & (gt_depth > 0).squeeze() & (err < 0.1).squeeze() & rm
+    depth_loss = torch.abs(err[valid]).mean()
+    ref = 1.0 * depth_loss + 0.8 * color_loss
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    assert abs(float(parts[1]) - float(color_loss)) < 1e-6 and abs(float(parts[2]) - float(depth_loss)) < 1e-6
+    assert int(parts[3]) == int(valid.sum())
+    assert float((g1 - render.grad).abs().max()) < 1e-9 + 1e-5 * float(render.grad.abs().max())
+    assert float((g2 - depth.grad).abs().max()) < 1e-9 + 1e-5 * float(depth.grad.abs().max())
