@@ -253,7 +253,9 @@ def main():
     campos_dev = [torch.empty(3, device=dev) for _ in range(2)]
     uploaded = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.zeros(1).pin_memory()
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses = []
     vcs = [types.SimpleNamespace(FoVx=2 * math.atan(cam.tanfovx), FoVy=2 * math.atan(cam.tanfovy), image_height=H, image_width=W,
                                  world_view_transform=view_dev[k][0], full_proj_transform=view_dev[k][1], camera_center=campos_dev[k],
                                  cx=cam.cx, cy=cam.cy) for k in range(2)]
@@ -287,18 +289,36 @@ def main():
         loss, _parts = l1_color_depth_loss(out, fd[:3], fd[3], color_weight=0.8, depth_weight=1.0, depth_error_max=0.1)
         loss.backward()
         consumed[k].record(cur)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)       # the loss.item() of mapper.py:459
-        return float(loss_host[0])
+        # the step's loss goes to pinned host memory (the loss.item() of mapper.py:459); it is *consumed* one step later,
+        # after the next step has been queued, so the device never idles while the host waits for a scalar
+        loss_host[k].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_ready[k].record(cur)
+        if state.get("pending") is not None:
+            j = state["pending"]
+            loss_ready[j].synchronize()
+            losses.append(float(loss_host[j][0]))
+        state["pending"] = k
+
+    def e2e_drain():
+        if state.get("pending") is not None:
+            j = state["pending"]
+            loss_ready[j].synchronize()
+            losses.append(float(loss_host[j][0]))
+            state["pending"] = None
 
     for _ in range(3):
         e2e_step()
+    e2e_drain()
     barrier()
+    n_before = len(losses)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    e2e_drain()  # the last step's loss is read inside the timed region too
     e1.record()
     barrier()
+    assert len(losses) - n_before == args.steps and all(math.isfinite(x) for x in losses), "every step's loss must reach the host"
     wall = (time.perf_counter() - t0) * 1e3
     tm = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev, dtype=torch.float64)
     if world > 1:
