@@ -209,6 +209,13 @@ __device__ __forceinline__ int pair_owner(const uint32_t *excl, uint32_t k) {
     return o;
 }
 
+// L2 prefetch of the 128-byte line(s) holding [p, p + bytes): issued as soon as an index is known, long before the
+// data is consumed, to overlap the DRAM latency with the arithmetic in between
+__device__ __forceinline__ void prefetch_l2(const void *p, int bytes) {
+    const char *c = reinterpret_cast<const char *>(p);
+    for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+}
+
 // explicit shared-state-space accesses with a precomputed 32-bit base (keeps address arithmetic out of the loops)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     uint32_t a = (uint32_t)__cvta_generic_to_shared(p);

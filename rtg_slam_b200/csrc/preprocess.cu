@@ -130,6 +130,7 @@ __device__ __forceinline__ bool preprocess_one(const ViewParams &vp, const int i
         radii[idx] = 0;
         return false;
     }
+    if (shs != nullptr) prefetch_l2(shs + (size_t)idx * 3 * M, 12 * M + 64);  // consumed ~300 instructions later
 
     float c6[6];
     float R[3][3];
@@ -437,6 +438,7 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
     float *dL_dmeans = o.dL_dmeans, *dL_dsh = o.dL_dsh, *dL_dcolors = o.dL_dcolors, *dL_dopacity = o.dL_dopacity,
           *dL_dscales = o.dL_dscales, *dL_drot = o.dL_drot, *dL_dcov3D = o.dL_dcov3D, *dL_dmeans2D = o.dL_dmeans2D;
 
+    if (has_sh) prefetch_l2(shs + (size_t)idx * 3 * M, 12 * M + 64);  // consumed inside bwd_sh
     // consume + clear the gradient record
     float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)idx * RTG_REC);
     const float4 ra = r4[0], rb = r4[1], rc = r4[2], rd = r4[3];

@@ -433,6 +433,10 @@ __global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParam
         A.dLp0 = insA ? dL_dcolor[pidA] : 0.f; A.dLp1 = insA ? dL_dcolor[N + pidA] : 0.f; A.dLp2 = insA ? dL_dcolor[2 * N + pidA] : 0.f;
         B.dLp0 = insB ? dL_dcolor[pidB] : 0.f; B.dLp1 = insB ? dL_dcolor[N + pidB] : 0.f; B.dLp2 = insB ? dL_dcolor[2 * N + pidB] : 0.f;
         A.bg_dot = bg0 * A.dLp0 + bg1 * A.dLp1 + bg2 * A.dLp2; B.bg_dot = bg0 * B.dLp0 + bg1 * B.dLp1 + bg2 * B.dLp2;
+        // a pixel whose upstream colour gradient is exactly zero (outside the render mask of the mapping loss) adds
+        // exact zeros to every colour-path term: skip its replay altogether
+        if (A.dLp0 == 0.f && A.dLp1 == 0.f && A.dLp2 == 0.f) A.last_contributor = 0u;
+        if (B.dLp0 == 0.f && B.dLp1 == 0.f && B.dLp2 == 0.f) B.last_contributor = 0u;
         A.accum0 = A.accum1 = A.accum2 = A.last_alpha = A.lc0 = A.lc1 = A.lc2 = 0.f;
         B.accum0 = B.accum1 = B.accum2 = B.last_alpha = B.lc0 = B.lc1 = B.lc2 = 0.f;
         A.pyf = (float)pyA; B.pyf = (float)pyB;

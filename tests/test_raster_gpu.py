@@ -121,6 +121,22 @@ def test_equal_depth_ties_follow_gaussian_index(cuda_device):
     check_against_oracle(cam, g, cuda_device, label="ties")
 
 
+def test_backward_with_masked_upstream_gradient(cuda_device):
+    """Mapping optimises with a render mask: dL/dcolour is exactly zero outside it (mapper.py:421). Those pixels are
+    skipped by the backward; the result must equal the full replay (they only add zeros)."""
+    cam = scene.make_camera("small")
+    g = scene.surfel_room(3000, seed=14)
+    gc, gd = scene.upstream_grads(cam, seed=5)
+    rng = np.random.default_rng(2)
+    keep = rng.uniform(size=(cam.height, cam.width)) < 0.4
+    gc = gc * keep[None]
+    ours = helpers.run_ours(cam, g, cuda_device, grads=(gc, gd))
+    o = OracleRender(cam, g, precision="f32")
+    og = o.backward(gc, gd)
+    for k in GRADS:
+        assert helpers.rel_err(ours["grads"][k], og[k]) < 1e-3, k
+
+
 def test_edge_cases(cuda_device):
     from rtg_slam_b200.rasterizer import GaussianRasterizer
     dev = cuda_device
