@@ -216,6 +216,14 @@ __device__ __forceinline__ void prefetch_l2(const void *p, int bytes) {
     for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, bypassing L1) and its group fences
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // explicit shared-state-space accesses with a precomputed 32-bit base (keeps address arithmetic out of the loops)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     uint32_t a = (uint32_t)__cvta_generic_to_shared(p);

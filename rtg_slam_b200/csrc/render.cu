@@ -69,11 +69,12 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                                                          float *__restrict__ out_depth, int *__restrict__ out_hit_color,
                                                          int *__restrict__ out_hit_depth, float *__restrict__ out_hcw,
                                                          float *__restrict__ out_hdw, float *__restrict__ out_T) {
-    __shared__ float4 s_s0[BATCH];
-    __shared__ float4 s_s1[BATCH];
-    __shared__ float4 s_rgb[BATCH];
-    __shared__ int s_id[BATCH];
-    __shared__ uint32_t s_mask[BATCH];
+    // two staging buffers: batch i+1 is gathered with cp.async while batch i is composited
+    __shared__ float4 s_s0[2 * BATCH];
+    __shared__ float4 s_s1[2 * BATCH];
+    __shared__ float4 s_rgb[2 * BATCH];
+    __shared__ int s_id[2 * BATCH];
+    __shared__ uint32_t s_mask[2 * BATCH];
 
     const int tile = (int)b.active[blockIdx.x];  // longest lists first
     int px, py;
@@ -121,31 +122,42 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
     float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
 
     const int rounds = (n + BATCH - 1) / BATCH;
+    // stage(batch, id): asynchronous gather of one list entry per thread into buffer (batch & 1)
+    auto stage = [&](const int batch, const int id) {
+        const uint32_t slot = (uint32_t)((batch & 1) * BATCH + threadIdx.x);
+        cp_async16(a_s0 + slot * 16, g.splat + 2 * (size_t)id);
+        cp_async16(a_s1 + slot * 16, g.splat + 2 * (size_t)id + 1);
+        cp_async16(a_rgb + slot * 16, g.rgb_flags + id);
+        sts32(a_id + slot * 4, (uint32_t)id);
+    };
+    if ((int)threadIdx.x < n) stage(0, (int)b.point_list[start + threadIdx.x]);
+    cp_async_commit();
+    int id_next = (BATCH + (int)threadIdx.x < n) ? (int)b.point_list[start + BATCH + threadIdx.x] : -1;  // ids one batch ahead
     for (int i = 0; i < rounds; i++) {
-        if (__syncthreads_count(done) == BATCH) break;
-        const int progress = i * BATCH + threadIdx.x;
-        if (progress < n) {
-            const int id = (int)b.point_list[start + progress];
-            const float4 s0 = __ldg(g.splat + 2 * (size_t)id), s1 = __ldg(g.splat + 2 * (size_t)id + 1);
-            s_id[threadIdx.x] = id;
-            s_s0[threadIdx.x] = s0;
-            s_s1[threadIdx.x] = s1;
-            s_rgb[threadIdx.x] = __ldg(g.rgb_flags + id);
-            s_mask[threadIdx.x] = patch_mask(s0, s1, tx0, ty0);
+        cp_async_wait_all();                                   // this thread's copies of batch i have landed
+        if (__syncthreads_count(done) == BATCH) break;          // everybody's have; and batch i-1 is fully consumed
+        const uint32_t boff = (uint32_t)((i & 1) * BATCH);
+        if (i * BATCH + (int)threadIdx.x < n) {
+            const float4 s0 = lds128(a_s0 + (boff + threadIdx.x) * 16), s1 = lds128(a_s1 + (boff + threadIdx.x) * 16);
+            sts32(a_mask + (boff + threadIdx.x) * 4, patch_mask(s0, s1, tx0, ty0));
         }
+        if (id_next >= 0) stage(i + 1, id_next);                // overlaps with the compositing of batch i
+        cp_async_commit();
+        id_next = ((i + 2) * BATCH + (int)threadIdx.x < n) ? (int)b.point_list[start + (i + 2) * BATCH + threadIdx.x] : -1;
         __syncthreads();
         const int cnt = min(BATCH, n - i * BATCH);
         if (__all_sync(FULL, done)) continue;  // warp-uniform
         const int chunks = (cnt + 31) >> 5;
         for (int c = 0; c < chunks; c++) {
             const int e = (c << 5) + lane;
-            const uint32_t mm = (e < cnt) ? lds32(a_mask + e * 4) : 0u;
+            const uint32_t mm = (e < cnt) ? lds32(a_mask + (boff + e) * 4) : 0u;
             uint32_t bits = __ballot_sync(FULL, (mm >> w) & 1u);
             while (bits) {
                 const int j = (c << 5) + __ffs(bits) - 1;
+                const uint32_t jb = boff + (uint32_t)j;
                 bits &= bits - 1;
                 if (!done) {
-                    const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
+                    const float4 s0 = lds128(a_s0 + jb * 16), s1 = lds128(a_s1 + jb * 16);
                     const float dx = s0.x - pixf.x, dy = s0.y - pixf.y;
                     const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
                     // power > 0: skipped by the reference; power < -q_cut: alpha is certainly below 1/255
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                         const float alpha = fminf(0.99f, s1.w * expf(power));
                         if (alpha >= 1.0f / 255.0f) {
                             if (!hit && alpha >= opaque_thr) {
-                                const int id = (int)lds32(a_id + j * 4);
+                                const int id = (int)lds32(a_id + jb * 4);
                                 depth_ = surfel_depth(__ldg(g.hit + 2 * (size_t)id), __ldg(g.hit + 2 * (size_t)id + 1), ray, s0.w,
                                                       vp.depth_thr, vp.normal_thr);
                                 hit_id = id;
@@ -167,11 +179,11 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                                 else T = test_T;
                             } else {
                                 const float cw = alpha * T;
-                                const float4 col = lds128(a_rgb + j * 16);
+                                const float4 col = lds128(a_rgb + jb * 16);
                                 C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
                                 if (cw > cw_max) {
                                     cw_max = cw;
-                                    hit_color_id = (int)lds32(a_id + j * 4);
+                                    hit_color_id = (int)lds32(a_id + jb * 4);
                                     hit_cw = cw;
                                 }
                                 last_contributor = (uint32_t)(i * BATCH + j + 1);
