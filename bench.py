@@ -365,8 +365,10 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(P, cam), "parallelism": "one frame per GPU per step on a replicated map (NCCL broadcast at start; no data-path collective)" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2: 236 MB of Gaussian parameters + 76 MB of splat records + 236 MB of gradients are streamed every step (L2 = 126 MB)",
+        "config": {"workload": workload_name(P, cam),
+                   "e2e": "per step: RGB-D frame (4xHxW fp32) + camera matrices copied from pinned host memory (double-buffered on a side stream), Renderer.render, fused L1 colour+depth loss, backward, loss copied to pinned host memory and read one step later; the Gaussian map stays resident, as in the SLAM loop",
+                   "parallelism": "one frame per GPU per step on a replicated map (NCCL broadcast at start; no data-path collective)" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: 236 MB of Gaussian parameters + 84 MB of splat records + 236 MB of gradients are streamed every step (L2 = 126 MB)",
                    "visible_gaussians": vis, "num_rendered": R, "active_tiles": n_tiles, "mean_tile_list": R / max(n_tiles, 1), "max_tile_list": int(counters[3])},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline,
@@ -513,6 +515,16 @@ def extras(dev, cam, t, leaves, step):
     ex["icp_iters_per_s"] = 15 / dt
     ex["icp_ms_per_predict_pose"] = dt * 1e3
     ex["icp_note"] = "IcpTracker.predict_pose, 1200x680, levels 0.25/0.5/1.0 x 5 iterations, incl. the final pose read-back"
+    # the same solve with the CPU restatement of the reference's SLAM/icp.py (numpy, host cores)
+    from oracle import icp_oracle
+    d0n, d1n = d0.cpu().numpy(), d1.cpu().numpy()
+    Kf = (cam.fx, cam.fy, cam.cx, cam.cy)
+    icp_oracle.predict_pose(d0n, d1n, Kf)
+    t0 = time.perf_counter()
+    pose_cpu, _, _, _ = icp_oracle.predict_pose(d0n, d1n, Kf)
+    ex["icp_cpu_port_iters_per_s"] = 15 / (time.perf_counter() - t0)
+    pose_gpu, _ = trk.predict_pose({"K": Kt, "frame_id": 1})
+    ex["icp_pose_diff_vs_cpu_port"] = float(np.linalg.norm(pose_gpu - pose_cpu))
     return ex
 
 
