@@ -455,6 +455,7 @@ def cpu_baseline(args, cam):
 
 
 def extras(dev, cam, t, leaves, step):
+    import math
     """Side measurements reported next to the headline: reference CUDA rasterizer on this GPU, Adam step, ICP."""
     import torch
     from rtg_slam_b200 import scene
@@ -492,6 +493,44 @@ def extras(dev, cam, t, leaves, step):
         ms = a.elapsed_time(b) / 10
         ex[f"adam_{name}_ms"] = ms
         ex[f"adam_{name}_GBps"] = 1652 * P / (ms * 1e-3) / 1e9
+    # BASELINE configs[2]: full optimisation iteration at 1920x1080 (render + loss + backward + Adam), same map
+    try:
+        from rtg_slam_b200.render import Renderer
+        from rtg_slam_b200.loss import l1_color_depth_loss
+        camh = scene.make_camera("hd")
+        rargs = types.SimpleNamespace(renderer_opaque_threshold=0.6, renderer_normal_threshold=60, renderer_depth_threshold=1.0,
+                                      max_sh_degree=3, color_sigma=3.0, active_sh_degree=3)
+        rend = Renderer(rargs)
+        vc = types.SimpleNamespace(FoVx=2 * math.atan(camh.tanfovx), FoVy=2 * math.atan(camh.tanfovy), image_height=camh.height,
+                                   image_width=camh.width, world_view_transform=torch.from_numpy(camh.viewmatrix).to(dev),
+                                   full_proj_transform=torch.from_numpy(camh.projmatrix).to(dev),
+                                   camera_center=torch.from_numpy(camh.campos).to(dev), cx=camh.cx, cy=camh.cy)
+        data = dict(xyz=leaves["xyz"], opacity=leaves["opacity"], scales=leaves["scales"], rotations=leaves["rotations"],
+                    shs=leaves["shs"], normal=t["normal"])
+        with torch.no_grad():
+            o0 = rend.render(vc, data)
+            gt_c, gt_d = (o0["render"] + 0.01).clone(), (o0["depth"][0] + 0.01).clone()
+        opt = FusedAdam([{"params": [leaves[k]], "lr": lr} for k, lr in (("xyz", 1e-6), ("shs", 1e-6), ("opacity", 0.0), ("scales", 1e-6), ("rotations", 1e-6))],
+                        lr=0.0, eps=1e-15)
+
+        def opt_step():
+            opt.zero_grad(set_to_none=True)
+            loss, _ = l1_color_depth_loss(rend.render(vc, data), gt_c, gt_d)
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            opt_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            opt_step()
+        b.record()
+        torch.cuda.synchronize()
+        ex["optimize_step_1920x1080_ms"] = a.elapsed_time(b) / 20
+        ex["optimize_step_note"] = "BASELINE configs[2]: 1 M Gaussians, 1920x1080, Renderer.render + fused L1 loss + backward + FusedAdam"
+    except Exception as e:
+        ex["optimize_step_1920x1080_ms"] = repr(e)
     # ICP: 3 levels x 5 iterations at this resolution
     from rtg_slam_b200 import icp as ricp
     cam1 = scene.make_camera("replica", c2w=scene.small_pose())

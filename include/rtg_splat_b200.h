@@ -89,7 +89,9 @@ int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const floa
  * `counters` are those of the matching forward call; `final_T` is the forward's out_T,
  * `hit_image` its out_hit_depth (__init__.py:172-235). `grad2d_scratch`: P*16 floats that must be
  * all-zero on entry and are left all-zero on exit. Optional outputs (may be NULL):
- * dL_dcolors_precomp, dL_dcov3D, dL_dmeans2D. */
+ * dL_dcolors_precomp, dL_dcov3D, dL_dmeans2D. Internally the zero-fill of the culled rows runs on a library-owned
+ * side stream that forks from and joins back into `stream` within this call (event fork/join, graph-capturable);
+ * to the caller all work is ordered on `stream`. */
 int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
                        const float *colors_precomp, const float *scales, const float *rotations,
                        const float *cov3D_precomp, const int32_t *radii, const void *geom_ws, const void *img_ws,

@@ -61,10 +61,28 @@ void prof_end(int id, cudaStream_t s) {
     g_prof_recs.push_back({id, t_open[id], e});
 }
 static const char *kKernelNames[K_COUNT] = {"preprocess_fwd", "tile_scan", "scatter", "tile_sort", "render_fwd", "render_bwd",
-                                            "preprocess_bwd", "adam", "icp_build_level", "icp_iter", "icp_misc"};
+                                            "preprocess_bwd", "adam", "icp_build_level", "icp_iter", "image_glue", "bwd_zero"};
 }  // namespace rtg
 
 static thread_local std::string g_err;
+
+// one non-blocking side stream (+ fork / join events) per device, created on first use
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream *side_stream() {
+    static std::mutex mu;
+    static SideStream table[64];
+    static bool made[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!made[dev]) {
+        if (cudaStreamCreateWithFlags(&table[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&table[dev].fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&table[dev].join, cudaEventDisableTiming);
+        made[dev] = true;
+    }
+    return &table[dev];
+}
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -213,10 +231,20 @@ int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const flo
     rtg::BinState b = rtg::bin_from(const_cast<void *>(bin_ws), (size_t)T, (size_t)R_cap);
     // counters live in the scan output: recompute the overflow word location is not needed -- the
     // backward reads the same device counters the forward wrote.
+    // fork: the zero-fill of the culled rows only depends on the forward; it streams to HBM on a side stream while
+    // the compute-bound render backward runs, and joins before the call's work on `s` ends
+    SideStream *ss = side_stream();
+    cudaError_t e = ss ? cudaEventRecord(ss->fork, s) : cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
+    const bool forked = (e == cudaSuccess);
+    rtg::launch_bwd_zero(P, M, shs != nullptr, cov3D_precomp == nullptr, radii, dL_dmeans3D, dL_dsh, dL_dcolors_precomp, dL_dopacity,
+                         dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, forked ? ss->stream : s);
+    if (forked) cudaEventRecord(ss->join, ss->stream);
     rtg::launch_render_bwd(vp, g, b, img, counters, means3D, scales, rotations, final_T, hit_image, dL_dcolor, dL_ddepth,
                            grad2d_scratch, s);
-    rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, radii, g, b.vis_count, grad2d_scratch, dL_dmeans3D,
+    rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, g, b.vis_count, grad2d_scratch, dL_dmeans3D,
                                dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, s);
+    if (forked) cudaStreamWaitEvent(s, ss->join, 0);
     return check_launch("rtg_splat_backward");
 }
 

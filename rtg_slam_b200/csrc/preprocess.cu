@@ -565,23 +565,14 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
 }
 
 
-// Two duties per CTA: (1) zero the gradients of the culled Gaussians of its own index range (light, streaming);
-// (2) run the full backward for one slice of the compact visible list built by the forward preprocess, so that the
-// register-heavy path executes with full warps instead of ~40 % of the lanes.
-__global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
-                                                                const float *__restrict__ means, const float *__restrict__ scales,
-                                                                const float *__restrict__ rots, const float *__restrict__ shs,
-                                                                const float *__restrict__ cov3D_precomp, const int *__restrict__ radii,
-                                                                const GeomState g, const uint32_t *__restrict__ vis_count,
-                                                                float *__restrict__ rec, const BwdOut o) {
-    __shared__ float s_m[40];
-    if (threadIdx.x < 16) s_m[threadIdx.x] = vp.view[threadIdx.x];
-    else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
-    else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
-    __syncthreads();
+// Zero gradients for the culled Gaussians (the reference zero-fills every gradient tensor first,
+// rasterize_points.cu:195-203). Pure streaming stores that depend on the forward only, so the C ABI runs this kernel
+// on a side stream, concurrently with the compute-bound render backward.
+__global__ void __launch_bounds__(256) bwd_zero_kernel(const int P, const int M, const bool has_sh, const bool has_sr,
+                                                       const int *__restrict__ radii, const BwdOut o) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool culled = idx < P && !(radii[idx] > 0);
-    const bool coop_sh = (shs != nullptr) && (M == 16);
+    const bool coop_sh = has_sh && (M == 16);
     if (coop_sh) {
         // the warp's 32 dL_dsh rows are one contiguous 6 KB block: zero the culled rows with fully coalesced stores
         const uint32_t cm = __ballot_sync(0xffffffffu, culled);
@@ -595,7 +586,23 @@ __global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(const ViewParams
             }
         }
     }
-    if (culled) bwd_zero(idx, M, shs != nullptr, cov3D_precomp == nullptr, o, coop_sh);
+    if (culled) bwd_zero(idx, M, has_sh, has_sr, o, coop_sh);
+}
+
+// Full backward for the compact visible list built by the forward preprocess: the register-heavy path runs with full
+// warps instead of ~40 % of the lanes.
+__global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
+                                                                const float *__restrict__ means, const float *__restrict__ scales,
+                                                                const float *__restrict__ rots, const float *__restrict__ shs,
+                                                                const float *__restrict__ cov3D_precomp, const GeomState g,
+                                                                const uint32_t *__restrict__ vis_count, float *__restrict__ rec,
+                                                                const BwdOut o) {
+    __shared__ float s_m[40];
+    if (threadIdx.x < 16) s_m[threadIdx.x] = vp.view[threadIdx.x];
+    else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t V = *vis_count;
     if ((uint32_t)idx < V) bwd_visible(vp, (int)g.vis_list[idx], M, s_m, means, scales, rots, shs, cov3D_precomp, g, rec, o);
 }
@@ -616,14 +623,22 @@ void launch_mark_visible(int P, const float *means, const float *view, const flo
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means, view, proj, present);
 }
 
+void launch_bwd_zero(int P, int M, bool has_sh, bool has_sr, const int *radii, float *dL_dmeans, float *dL_dsh, float *dL_dcolors,
+                     float *dL_dopacity, float *dL_dscales, float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s) {
+    if (P <= 0) return;
+    ProfScope ps(K_BWD_ZERO, s);
+    BwdOut o{dL_dmeans, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drot, dL_dcov3D, dL_dmeans2D};
+    bwd_zero_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, M, has_sh, has_sr, radii, o);
+}
+
 void launch_preprocess_bwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
-                           const float *shs, const float *cov3D_precomp, const int *radii, const GeomState &g,
-                           const uint32_t *vis_count, float *rec, float *dL_dmeans, float *dL_dsh, float *dL_dcolors,
-                           float *dL_dopacity, float *dL_dscales, float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s) {
+                           const float *shs, const float *cov3D_precomp, const GeomState &g, const uint32_t *vis_count, float *rec,
+                           float *dL_dmeans, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales, float *dL_drot,
+                           float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s) {
     if (P <= 0) return;
     ProfScope ps(K_PREPROCESS_BWD, s);
     BwdOut o{dL_dmeans, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drot, dL_dcov3D, dL_dmeans2D};
-    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, shs, cov3D_precomp, radii, g, vis_count, rec, o);
+    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, shs, cov3D_precomp, g, vis_count, rec, o);
 }
 
 }  // namespace rtg

@@ -371,7 +371,7 @@ __device__ __forceinline__ bool bwd_pair(BwdPix &p, const uint32_t pos, const fl
     const float G = expf(power);
     const float alpha = fminf(0.99f, s1.w * G);
     if (alpha < 1.0f / 255.0f) return false;
-    const float inv_1ma = __frcp_rn(1.f - alpha);
+    const float inv_1ma = __fdividef(1.f, 1.f - alpha);  // 1 - alpha is in [0.01, 0.996]: the fast reciprocal is exact to 2 ulp
     p.T = p.T * inv_1ma;
     const float dch = alpha * p.T;
     const float4 col = lds128(a_rgb_j);
