@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtg_splat_b200.so")
+# RTG_SPLAT_LIB: developer knob for A/B-ing kernel variants built by tools/build_variant.py
+LIB_PATH = os.environ.get("RTG_SPLAT_LIB") or os.path.join(HERE, "librtg_splat_b200.so")
 
 RTG_CNT_WORDS = 8
 RTG_ADAM_MAX_GROUPS = 8

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
                                                       const int *__restrict__ counters) {
     __shared__ uint32_t s_excl[8][32], s_rect[8][32];
     __shared__ float4 s_ga[8][32], s_gb[8][32];
+    __shared__ uint32_t s_depth[8][32];
     if (counters[2]) return;  // capacity overflow: render nothing, the caller retries with a larger buffer
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -112,25 +113,29 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
     if (total == 0) return;  // warp-uniform
     s_excl[w][lane] = (uint32_t)(incl - npairs);
     s_rect[w][lane] = pack_rect(x0, y0, max(x1 - x0, 1));
-    s_ga[w][lane] = s0;  // x, y, q_cut, depth
-    s_gb[w][lane] = s1;  // conic, opacity
+    const float2 nb = cut_slopes(s1.x, s1.y, s1.z);
+    s_ga[w][lane] = make_float4(s0.x, s0.y, s0.z, nb.x);  // x, y, q_cut, -b/c
+    s_gb[w][lane] = make_float4(s1.x, s1.y, s1.z, nb.y);  // conic, -b/a
+    s_depth[w][lane] = __float_as_uint(s0.w);
     __syncwarp();
     const int base = idx - lane;
     for (int k = lane; k < total; k += 32) {
         const int o = pair_owner(s_excl[w], (uint32_t)k);
         const uint32_t local = (uint32_t)k - s_excl[w][o], rc = s_rect[w][o];
         const uint32_t rw = rc >> 20;
-        const int x = (int)(rc & 1023u) + (int)(local % rw), y = (int)((rc >> 10) & 1023u) + (int)(local / rw);
+        int cx, cy;
+        rect_cell(local, rw, cx, cy);
+        const int x = (int)(rc & 1023u) + cx, y = (int)((rc >> 10) & 1023u) + cy;
         const int t = y * vp.tiles_x + x;
         if (__ldg(tile_mask + t)) {
             const float4 ga = s_ga[w][o], gb = s_gb[w][o];
             const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
             // same (bit-identical) decision as the histogram pass in preprocess_fwd_kernel
-            if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
+            if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, ga.w, gb.w, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
             const uint32_t slot = atomicAdd(b.tile_fill + t, 1u);
             const uint32_t begin = b.tile_offset[t];
             if (slot < b.tile_offset[t + 1] - begin)  // never write outside the bucket
-                b.keys[begin + slot] = ((uint64_t)__float_as_uint(ga.w) << 32) | (uint32_t)(base + o);
+                b.keys[begin + slot] = ((uint64_t)s_depth[w][o] << 32) | (uint32_t)(base + o);
         }
     }
 }
@@ -139,35 +144,104 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
 #define SORT_THREADS 256
 #define SORT_SMEM_KEYS 4096
 
-__device__ __forceinline__ void bitonic_sort(uint64_t *k, const int N, const int tid, const int nthreads) {
-    for (int size = 2; size <= N; size <<= 1) {
-        for (int j = size >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < (N >> 1); i += nthreads) {
-                const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int c = a | j;
-                const bool up = ((a & size) == 0);
-                const uint64_t x = k[a], y = k[c];
-                if ((x > y) == up) { k[a] = y; k[c] = x; }
-            }
-            // Pair i touches keys inside the 64-key segment [64*(i/32), +63] whenever j <= 32, and thread t always
-            // handles the pairs i = t + m*nthreads, so a warp owns the same segments in every such sub-stage: a
-            // warp-level barrier is enough unless this or the next sub-stage crosses segments.
-            const int jn = (j > 1) ? (j >> 1) : size;  // stride of the next sub-stage
-            if (j > 32 || jn > 32) __syncthreads();
-            else __syncwarp();
-        }
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ int next_pow2(int n) {
     int N = 1;
     while (N < n) N <<= 1;
     return N;
 }
 
-// One CTA per non-empty tile. Up to SORT_SMEM_KEYS keys are sorted in one go in 32 KB of shared memory. Longer
-// lists (rare: a few tiles in front of a dense surface) are sorted chunk by chunk and merged by rank: with chunk c
+// Register-resident bitonic sort of 256*K keys by one CTA of 256 threads: thread t holds the keys of positions
+// t*K .. t*K+K-1. A compare-exchange sub-stage with partner distance j is
+//   j <  K      : both keys in the same thread  -> register compare-swap with compile-time indices,
+//   j <  32*K   : partner in the same warp       -> one 64-bit shuffle,
+//   j >= 32*K   : partner in another warp        -> one pass through shared memory (striped: conflict-free),
+// so only 6 of the 55 (N = 1024) .. 78 (N = 4096) sub-stages touch shared memory at all. `Nn` (a power of two,
+// >= the number of real keys) bounds the merge size: blocks beyond it hold only +inf padding.
+template <int K>
+__device__ __forceinline__ void sort_in_registers(uint64_t (&key)[K], const int Nn, uint64_t *s_buf) {
+    const int t = threadIdx.x;
+    const int base = t * K;
+    for (int size = 2; size <= Nn; size <<= 1) {
+        const bool up_t = ((base & size) == 0);  // direction of this thread's keys when size >= K
+        int j = size >> 1;
+        for (; j >= 32 * K; j >>= 1) {
+            const int tj = j / K;                  // partner thread = t ^ tj
+            __syncthreads();                       // the previous pass has been read by everybody
+#pragma unroll
+            for (int r = 0; r < K; r++) s_buf[r * SORT_THREADS + t] = key[r];
+            __syncthreads();
+            const bool keep_min = (((t & tj) == 0) == up_t);
+#pragma unroll
+            for (int r = 0; r < K; r++) {
+                const uint64_t o = s_buf[r * SORT_THREADS + (t ^ tj)];
+                const bool o_less = o < key[r];
+                key[r] = (o_less == keep_min) ? o : key[r];
+            }
+        }
+        for (; j >= K; j >>= 1) {
+            const int lj = j / K;                  // partner lane = lane ^ lj
+            const bool keep_min = (((t & lj) == 0) == up_t);
+#pragma unroll
+            for (int r = 0; r < K; r++) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, key[r], lj);
+                const bool o_less = o < key[r];
+                key[r] = (o_less == keep_min) ? o : key[r];
+            }
+        }
+#pragma unroll
+        for (int jj = K / 2; jj > 0; jj >>= 1) {
+            if (jj < size) {
+#pragma unroll
+                for (int r = 0; r < K; r++) {
+                    if ((r & jj) == 0) {
+                        const bool up = (((base + r) & size) == 0);
+                        const uint64_t x = key[r], y = key[r | jj];
+                        const bool sw = (x > y) == up;
+                        key[r] = sw ? y : x;
+                        key[r | jj] = sw ? x : y;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Load (any order: the input is unsorted), sort, write front to back either the Gaussian ids of the n real keys
+// (IDS) or the sorted keys themselves, in place (chunks of an oversized list). K must be the smallest power of two
+// with n <= 256*K, so that next_pow2(n) covers every position that holds a real key.
+template <int K, bool IDS>
+__device__ __forceinline__ void sort_tile_in_registers(uint64_t *__restrict__ gk, uint32_t *__restrict__ out, const int n,
+                                                       uint64_t *s_buf) {
+    uint64_t key[K];
+#pragma unroll
+    for (int r = 0; r < K; r++) {
+        const int i = r * SORT_THREADS + (int)threadIdx.x;  // coalesced
+        key[r] = (i < n) ? gk[i] : 0xffffffffffffffffull;
+    }
+    if (!IDS) __syncthreads();  // in place: everybody has read its keys before sorted keys are written back
+    sort_in_registers<K>(key, K == 1 ? next_pow2(n) : SORT_THREADS * K, s_buf);
+#pragma unroll
+    for (int r = 0; r < K; r++) {
+        const int i = (int)threadIdx.x * K + r;
+        if (i < n) {
+            if (IDS) out[i] = (uint32_t)key[r];
+            else gk[i] = key[r];
+        }
+    }
+}
+
+template <bool IDS>
+__device__ __forceinline__ void sort_up_to_4096(uint64_t *__restrict__ gk, uint32_t *__restrict__ out, const int n, uint64_t *s_buf) {
+    if (n <= 256) sort_tile_in_registers<1, IDS>(gk, out, n, s_buf);
+    else if (n <= 512) sort_tile_in_registers<2, IDS>(gk, out, n, s_buf);
+    else if (n <= 1024) sort_tile_in_registers<4, IDS>(gk, out, n, s_buf);
+    else if (n <= 2048) sort_tile_in_registers<8, IDS>(gk, out, n, s_buf);
+    else sort_tile_in_registers<16, IDS>(gk, out, n, s_buf);
+    __syncthreads();
+}
+
+// One CTA per non-empty tile. Up to SORT_SMEM_KEYS keys are sorted in registers (above). Longer lists (rare: a few
+// tiles in front of a dense surface) are sorted chunk by chunk in shared memory and merged by rank: with chunk c
 // resident (sorted) in shared memory, every key of the tile adds the number of chunk-c keys below it (binary
 // search on chip; keys are unique), which is its final position once all chunks have been visited.
 __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(BinState b, const int *__restrict__ counters) {
@@ -181,23 +255,13 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(BinState b, con
         uint64_t *gk = b.keys + start;
         uint32_t *out = b.point_list + start;
         if (n <= SORT_SMEM_KEYS) {
-            const int N = next_pow2(n);
-            for (int i = threadIdx.x; i < N; i += SORT_THREADS) s_keys[i] = (i < n) ? gk[i] : 0xffffffffffffffffull;
-            __syncthreads();
-            bitonic_sort(s_keys, N, threadIdx.x, SORT_THREADS);
-            for (int i = threadIdx.x; i < n; i += SORT_THREADS) out[i] = (uint32_t)s_keys[i];
-            __syncthreads();
+            sort_up_to_4096<true>(gk, out, n, s_keys);
             continue;
         }
         const int nchunks = (n + SORT_SMEM_KEYS - 1) / SORT_SMEM_KEYS;
         for (int c = 0; c < nchunks; c++) {  // sort every chunk in place
             const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);
-            const int N = next_pow2(cn);
-            for (int i = threadIdx.x; i < N; i += SORT_THREADS) s_keys[i] = (i < cn) ? gk[c0 + i] : 0xffffffffffffffffull;
-            __syncthreads();
-            bitonic_sort(s_keys, N, threadIdx.x, SORT_THREADS);
-            for (int i = threadIdx.x; i < cn; i += SORT_THREADS) gk[c0 + i] = s_keys[i];
-            __syncthreads();
+            sort_up_to_4096<false>(gk + c0, nullptr, cn, s_keys);
         }
         for (int c = 0; c < nchunks; c++) {  // accumulate ranks in `out` (used as scratch until the final permutation)
             const int c0 = c * SORT_SMEM_KEYS, cn = min(SORT_SMEM_KEYS, n - c0);

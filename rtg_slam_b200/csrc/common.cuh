@@ -155,8 +155,10 @@ __device__ __forceinline__ float q_cutoff(float opacity) {
 // Exact minimisation of the convex quadratic over the rectangle (centre inside -> 0, else the minimum lies on
 // one of the four edges). Written with explicit round-to-nearest intrinsics so that every kernel that
 // evaluates it (histogram, scatter, per-warp masks) takes bit-identical decisions.
-__device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, float b, float c, float q_cut, float x0, float x1,
-                                                  float y0, float y1) {
+// `nb_c` = -b/c and `nb_a` = -b/a (cut_slopes) are per-Gaussian: callers that test many rectangles pass them in.
+__device__ __forceinline__ float2 cut_slopes(float a, float b, float c) { return make_float2(__fdiv_rn(-b, c), __fdiv_rn(-b, a)); }
+__device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, float b, float c, float q_cut, float nb_c, float nb_a,
+                                                  float x0, float x1, float y0, float y1) {
     if (q_cut < 0.f) return true;
     if (!(a > 0.f) || !(c > 0.f)) return false;  // not a proper conic: keep the reference's behaviour
     const float dxl = __fsub_rn(gx, x1), dxh = __fsub_rn(gx, x0), dyl = __fsub_rn(gy, y1), dyh = __fsub_rn(gy, y0);
@@ -167,7 +169,6 @@ __device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, f
         const float q0 = __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy))));
         if (q0 <= q_cut) return false;
     }
-    const float nb_c = __fdiv_rn(-b, c), nb_a = __fdiv_rn(-b, a);
     float qmin;
     {
         const float dx = dxl, dy = fminf(dyh, fmaxf(dyl, __fmul_rn(nb_c, dx)));
@@ -193,6 +194,12 @@ __device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, f
 // warp share the pairs evenly instead of each lane looping over its own rectangle. `excl` / `rect` are the warp's
 // 32-entry shared arrays: exclusive prefix of the pair counts, and x0 | y0 << 10 | width << 20.
 __device__ __forceinline__ uint32_t pack_rect(int x0, int y0, int w) { return (uint32_t)x0 | ((uint32_t)y0 << 10) | ((uint32_t)w << 20); }
+// (column, row) of pair `local` inside a rectangle `rw` tiles wide, without an integer division: (local + 0.5) / rw is at
+// least 0.5 / rw away from an integer and the quotients are below 2^10, so the fp32 product truncates to the exact row.
+__device__ __forceinline__ void rect_cell(uint32_t local, uint32_t rw, int &dx, int &dy) {
+    dy = __float2int_rz(((float)local + 0.5f) * __frcp_rn((float)rw));
+    dx = (int)local - dy * (int)rw;
+}
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

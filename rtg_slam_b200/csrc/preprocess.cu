@@ -232,7 +232,10 @@ __device__ __forceinline__ bool preprocess_one(const ViewParams &vp, const int i
     return true;
 }
 
-__global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(const ViewParams vp, const int P, const int M,
+#ifndef PFWD_MIN_BLOCKS
+#define PFWD_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(const ViewParams vp, const int P, const int M,
                                                              const float *__restrict__ means, const float *__restrict__ scales,
                                                              const float *__restrict__ rots, const float *__restrict__ opac,
                                                              const float *__restrict__ shs, const float *__restrict__ colors_precomp,
@@ -275,20 +278,23 @@ __global__ void __launch_bounds__(256, 3) preprocess_fwd_kernel(const ViewParams
     s_excl[w][lane] = (uint32_t)(incl - npairs);
     if (valid) {
         s_rect[w][lane] = pack_rect(st.x0, st.y0, st.x1 - st.x0);
-        s_ga[w][lane] = make_float4(st.pix.x, st.pix.y, st.q_cut, 0.f);
-        s_gb[w][lane] = make_float4(st.conic.x, st.conic.y, st.conic.z, 0.f);
+        const float2 nb = cut_slopes(st.conic.x, st.conic.y, st.conic.z);
+        s_ga[w][lane] = make_float4(st.pix.x, st.pix.y, st.q_cut, nb.x);
+        s_gb[w][lane] = make_float4(st.conic.x, st.conic.y, st.conic.z, nb.y);
     }
     __syncwarp();
     for (int k = lane; k < total; k += 32) {
         const int o = pair_owner(s_excl[w], (uint32_t)k);
         const uint32_t local = (uint32_t)k - s_excl[w][o], rc = s_rect[w][o];
         const uint32_t rw = rc >> 20;
-        const int x = (int)(rc & 1023u) + (int)(local % rw), y = (int)((rc >> 10) & 1023u) + (int)(local / rw);
+        int cx, cy;
+        rect_cell(local, rw, cx, cy);
+        const int x = (int)(rc & 1023u) + cx, y = (int)((rc >> 10) & 1023u) + cy;
         const int tt = y * vp.tiles_x + x;
         if (__ldg(tile_mask + tt)) {
             const float4 ga = s_ga[w][o], gb = s_gb[w][o];
             const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
-            if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1)))
+            if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, ga.w, gb.w, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1)))
                 tile_touched[tt] = 1u;
             else
                 atomicAdd(tile_count + tt, 1u);
@@ -591,7 +597,11 @@ __global__ void __launch_bounds__(256) bwd_zero_kernel(const int P, const int M,
 
 // Full backward for the compact visible list built by the forward preprocess: the register-heavy path runs with full
 // warps instead of ~40 % of the lanes.
-__global__ void __launch_bounds__(256, 3) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
+#define PBWD_THREADS 256
+#ifndef PBWD_MIN_BLOCKS
+#define PBWD_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(PBWD_THREADS, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(const ViewParams vp, const int P, const int M,
                                                                 const float *__restrict__ means, const float *__restrict__ scales,
                                                                 const float *__restrict__ rots, const float *__restrict__ shs,
                                                                 const float *__restrict__ cov3D_precomp, const GeomState g,
@@ -638,7 +648,7 @@ void launch_preprocess_bwd(const ViewParams &vp, int P, int M, const float *mean
     if (P <= 0) return;
     ProfScope ps(K_PREPROCESS_BWD, s);
     BwdOut o{dL_dmeans, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drot, dL_dcov3D, dL_dmeans2D};
-    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, shs, cov3D_precomp, g, vis_count, rec, o);
+    preprocess_bwd_kernel<<<(P + PBWD_THREADS - 1) / PBWD_THREADS, PBWD_THREADS, 0, s>>>(vp, P, M, means, scales, rots, shs, cov3D_precomp, g, vis_count, rec, o);
 }
 
 }  // namespace rtg

@@ -40,10 +40,11 @@ __device__ __forceinline__ void pixel_of(const ViewParams &vp, int tile, int &px
 // bit k set <=> the Gaussian can pass the alpha cut-off somewhere in patch k of the tile at (tx0, ty0)
 __device__ __forceinline__ uint32_t patch_mask(const float4 s0, const float4 s1, float tx0, float ty0) {
     uint32_t m = 0;
+    const float2 nb = cut_slopes(s1.x, s1.y, s1.z);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const float x0 = tx0 + (float)((k & 1) * 8), y0 = ty0 + (float)((k >> 1) * 4);
-        if (!rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, x0, x0 + 7.f, y0, y0 + 3.f)) m |= (1u << k);
+        if (!rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, nb.x, nb.y, x0, x0 + 7.f, y0, y0 + 3.f)) m |= (1u << k);
     }
     return m;
 }
@@ -371,7 +372,8 @@ __device__ __forceinline__ bool bwd_pair(BwdPix &p, const uint32_t pos, const fl
     const float G = expf(power);
     const float alpha = fminf(0.99f, s1.w * G);
     if (alpha < 1.0f / 255.0f) return false;
-    const float inv_1ma = __fdividef(1.f, 1.f - alpha);  // 1 - alpha is in [0.01, 0.996]: the fast reciprocal is exact to 2 ulp
+    float inv_1ma;  // 1 - alpha is in [0.01, 0.996]: the bare MUFU.RCP (no range fix-up code) is exact to 1 ulp there
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
     p.T = p.T * inv_1ma;
     const float dch = alpha * p.T;
     const float4 col = lds128(a_rgb_j);
@@ -478,10 +480,11 @@ __global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParam
                 s_s1[q] = s1;
                 s_rgb[q] = __ldg(g.rgb_flags + id);
                 uint32_t mk = 0;
+                const float2 nb = cut_slopes(s1.x, s1.y, s1.z);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const float x0 = tx0 + (float)((k & 1) * 8), y0 = ty0 + (float)((k >> 1) * 8);
-                    if (!rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, x0, x0 + 7.f, y0, y0 + 7.f)) mk |= (1u << k);
+                    if (!rect_below_cutoff(s0.x, s0.y, s1.x, s1.y, s1.z, s0.z, nb.x, nb.y, x0, x0 + 7.f, y0, y0 + 7.f)) mk |= (1u << k);
                 }
                 s_mask[q] = mk;
             }

@@ -9,6 +9,12 @@ What shards and what does not (DESIGN.md "Multi-GPU"):
   gives every rank its frames, no collective is on that path;
 * the per-Gaussian gradients of the frames processed in one step are summed with ONE all-reduce over a single flat
   buffer (`FlatGrads`) before the (identical, replicated) Adam step -- the only exchange step of the loop;
+* TILES shard (single-frame strong scaling, SURVEY.md section 8(e) "literal first version"): compositing is
+  independent per 16x16 tile, so `TileShard` gives every rank an interleaved (or load-balanced) subset of the tiles
+  as the rasterizer's own `tile_mask` (RAST/.../__init__.py:210, forward.cu:660); every rank renders and
+  back-propagates only its tiles against the replicated map, the image pieces are disjoint (`TileShard.gather`
+  reassembles them when the full image is needed; the loss can stay shard-wise) and the per-Gaussian gradients are
+  partial sums that the same flat all-reduce completes;
 * ICP is a 27-number reduction per iteration at <= 0.8 Mpx: replicas only, never sharded.
 """
 from __future__ import annotations
@@ -77,6 +83,64 @@ class FlatGrads:
         if average and not async_op:
             self.flat.div_(world())
         return work
+
+
+class TileShard:
+    """Ownership of the 16x16 tiles of one frame by the ranks of the job.
+
+    `mask` (th, tw) int32 is what the rank passes to the rasterizer as `tile_mask` (AND-ed with the caller's own mask,
+    e.g. the mapper's transmission / colour-error masks); `pixel_mask` (H, W) bool selects the pixels the rank owns.
+    Ownership is a pure function of (tile grid, world size, weights): every rank computes the same table without
+    communicating. Without weights tiles are dealt round robin along the row-major tile index (neighbouring tiles
+    have similar list lengths, so this already balances well); with per-tile `weights` (e.g. the list lengths of
+    the previous iteration) tiles are dealt longest-first to the least loaded rank (LPT)."""
+
+    TILE = 16
+
+    def __init__(self, H: int, W: int, world_size: int | None = None, r: int | None = None, base_mask: torch.Tensor | None = None,
+                 weights: torch.Tensor | None = None, device="cpu"):
+        self.H, self.W = H, W
+        self.world = world() if world_size is None else world_size
+        self.rank = rank() if r is None else r
+        th, tw = (H + self.TILE - 1) // self.TILE, (W + self.TILE - 1) // self.TILE
+        self.tile_grid = (th, tw)
+        self.owner = self._owners(th * tw, self.world, weights).view(th, tw)
+        mine = self.owner == self.rank
+        if base_mask is not None:
+            mine = mine & (base_mask.to("cpu") != 0)
+        self.mask = mine.to(torch.int32).contiguous().to(device)
+        self.pixel_mask = mine.repeat_interleave(self.TILE, 0).repeat_interleave(self.TILE, 1)[:H, :W].contiguous().to(device)
+
+    @staticmethod
+    def _owners(n_tiles: int, w: int, weights: torch.Tensor | None) -> torch.Tensor:
+        if weights is None:
+            return torch.arange(n_tiles, dtype=torch.int64) % w
+        wt = weights.detach().to("cpu", torch.float64).reshape(-1)
+        assert wt.numel() == n_tiles
+        order = torch.argsort(wt, descending=True, stable=True).tolist()
+        load = [0.0] * w
+        owner = torch.empty(n_tiles, dtype=torch.int64)
+        for t in order:
+            r = min(range(w), key=lambda k: (load[k], k))
+            owner[t] = r
+            load[r] += float(wt[t])
+        return owner
+
+    def gather(self, img: torch.Tensor, fill: float = 0.0) -> torch.Tensor:
+        """Full image from the ranks' disjoint pieces: pixels a rank does not own are replaced by zero, one SUM
+        all-reduce, then `fill` is restored where nobody rendered (the rasterizer writes 0 / T=1 in tiles that are
+        masked out, so pass fill=1 for the transmittance map)."""
+        own = self.pixel_mask
+        piece = torch.where(own, img, torch.zeros((), dtype=img.dtype, device=img.device))
+        if self.world > 1:
+            dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+            covered = own.to(torch.int32)
+            dist.all_reduce(covered, op=dist.ReduceOp.SUM)
+        else:
+            covered = own.to(torch.int32)
+        if fill != 0.0:
+            piece = torch.where(covered > 0, piece, torch.full((), fill, dtype=img.dtype, device=img.device))
+        return piece
 
 
 def assert_replicas_equal(tensors: Sequence[torch.Tensor], atol: float = 0.0) -> None:

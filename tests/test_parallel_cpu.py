@@ -98,3 +98,84 @@ def test_shard_frames_and_flat_layout_single_process():
     fg.views["opacities"].fill_(2.0)
     assert fg.flat.sum().item() == 10.0
     assert fg.allreduce() is None  # no process group: no-op
+
+
+# ---------------------------------------------------------------------------------------------- tile sharding
+def _tile_worker(rank, world, port, q):
+    """One frame, tiles dealt to the ranks: rendering (oracle) only the own tiles, the gathered image equals the
+    single-process image and the all-reduced partial gradients equal the single-process gradients."""
+    from oracle.splat_oracle import OracleRender
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P = 600
+        g = scene.surfel_room(P, seed=11)
+        cam = scene.make_camera("tiny")
+        th, tw = cam.tile_grid
+        base = torch.ones(th, tw, dtype=torch.int32)
+        base[0, 0] = 0  # a tile the caller itself masks out stays masked on every rank
+        shard = parallel.TileShard(cam.height, cam.width, base_mask=base)
+        o = OracleRender(cam, g, tile_mask=shard.mask.numpy(), precision="f32")
+        color, depth, T = (torch.from_numpy(np.array(a)) for a in (o.color, o.depth, o.T_map))
+        gc, gd = scene.upstream_grads(cam, seed=5)
+        gr = o.backward(gc, gd)
+        o.close()
+        fg = parallel.FlatGrads(P, "cpu")
+        fg.accumulate({k: torch.from_numpy(gr[k]) for k in ("means3D", "shs", "opacities", "scales", "rotations")})
+        fg.allreduce()
+        full = (shard.gather(color), shard.gather(depth), shard.gather(T, fill=1.0))
+        q.put((rank, int(shard.mask.sum()), [f.numpy() for f in full], {k: v.clone().numpy() for k, v in fg.views.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_tile_sharded_frame():
+    from oracle.splat_oracle import OracleRender
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tile_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = scene.surfel_room(600, seed=11)
+    cam = scene.make_camera("tiny")
+    th, tw = cam.tile_grid
+    base = np.ones((th, tw), np.int32)
+    base[0, 0] = 0
+    assert res[0][1] + res[1][1] == th * tw - 1 and abs(res[0][1] - res[1][1]) <= 1
+    o = OracleRender(cam, g, tile_mask=base, precision="f32")
+    gr = o.backward(*scene.upstream_grads(cam, seed=5))
+    for r in res:  # every rank ends up with the full image and the full gradient
+        assert np.array_equal(r[2][0], o.color) and np.array_equal(r[2][1], o.depth) and np.array_equal(r[2][2], o.T_map)
+        for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+            ref = gr[k].reshape(r[3][k].shape)
+            assert np.allclose(r[3][k], ref, rtol=1e-4, atol=1e-9 + 1e-6 * np.abs(ref).max()), k
+    assert np.abs(gr["means3D"]).max() > 0
+    o.close()
+
+
+def test_tile_shard_tables():
+    H, W = 680, 1200
+    shards = [parallel.TileShard(H, W, 4, r) for r in range(4)]
+    total = sum(s.mask for s in shards)
+    assert torch.equal(total, torch.ones_like(total))  # a partition
+    assert max(int(s.mask.sum()) for s in shards) - min(int(s.mask.sum()) for s in shards) <= 1
+    union = torch.zeros(H, W, dtype=torch.int32)
+    for s in shards:
+        union += s.pixel_mask.to(torch.int32)
+    assert torch.equal(union, torch.ones_like(union))
+    # weighted (LPT) dealing: deterministic, a partition, and balanced to within the largest weight
+    wts = torch.rand(43 * 75, generator=torch.Generator().manual_seed(0)) ** 4
+    lpt = [parallel.TileShard(H, W, 4, r, weights=wts) for r in range(4)]
+    assert torch.equal(sum(s.mask for s in lpt), torch.ones_like(total))
+    loads = [float((wts.view(43, 75) * s.mask).sum()) for s in lpt]
+    assert max(loads) - min(loads) <= float(wts.max()) + 1e-9
+    assert torch.equal(lpt[1].mask, parallel.TileShard(H, W, 4, 1, weights=wts).mask)
+    # single process: gather is the identity on owned pixels
+    img = torch.rand(3, H, W)
+    assert torch.equal(parallel.TileShard(H, W, 1, 0).gather(img), img)
