@@ -152,42 +152,28 @@ __device__ __forceinline__ float q_cutoff(float opacity) {
 
 // True if q(d) = 0.5*(a dx^2 + c dy^2) + b dx dy > q_cut for EVERY point of the pixel rectangle
 // [x0,x1] x [y0,y1] (d = centre - pixel), i.e. the Gaussian cannot pass the alpha cut-off anywhere in it.
-// Exact minimisation of the convex quadratic over the rectangle (centre inside -> 0, else the minimum lies on
-// one of the four edges). Written with explicit round-to-nearest intrinsics so that every kernel that
-// evaluates it (histogram, scatter, per-warp masks) takes bit-identical decisions.
+// Exact minimisation of the convex quadratic over the rectangle: with the centre outside, the minimum lies on a
+// boundary edge that faces the centre (q decreases along the segment from any point of a far edge towards the
+// centre), so two line minimisations suffice: along the vertical line through the rectangle point nearest to the
+// centre and along the horizontal one. When the centre is inside the x (y) range, that line passes through the
+// nearest point itself and its minimum is dominated by the other line's; with the centre inside the rectangle
+// both give 0. Written with explicit round-to-nearest intrinsics so that every kernel that evaluates it
+// (histogram, scatter, per-warp masks) takes bit-identical decisions.
 // `nb_c` = -b/c and `nb_a` = -b/a (cut_slopes) are per-Gaussian: callers that test many rectangles pass them in.
 __device__ __forceinline__ float2 cut_slopes(float a, float b, float c) { return make_float2(__fdiv_rn(-b, c), __fdiv_rn(-b, a)); }
+__device__ __forceinline__ float cut_q(float a, float b, float c, float dx, float dy) {
+    return __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy))));
+}
 __device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, float b, float c, float q_cut, float nb_c, float nb_a,
                                                   float x0, float x1, float y0, float y1) {
     if (q_cut < 0.f) return true;
     if (!(a > 0.f) || !(c > 0.f)) return false;  // not a proper conic: keep the reference's behaviour
     const float dxl = __fsub_rn(gx, x1), dxh = __fsub_rn(gx, x0), dyl = __fsub_rn(gy, y1), dyh = __fsub_rn(gy, y0);
-    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return false;
-    {
-        // quick accept: q at the rectangle point nearest to the centre already passes -> the minimum passes too
-        const float dx = fminf(dxh, fmaxf(dxl, 0.f)), dy = fminf(dyh, fmaxf(dyl, 0.f));
-        const float q0 = __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy))));
-        if (q0 <= q_cut) return false;
-    }
-    float qmin;
-    {
-        const float dx = dxl, dy = fminf(dyh, fmaxf(dyl, __fmul_rn(nb_c, dx)));
-        qmin = __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy))));
-    }
-    {
-        const float dx = dxh, dy = fminf(dyh, fmaxf(dyl, __fmul_rn(nb_c, dx)));
-        qmin = fminf(qmin, __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy)))));
-    }
-    {
-        const float dy = dyl, dx = fminf(dxh, fmaxf(dxl, __fmul_rn(nb_a, dy)));
-        qmin = fminf(qmin, __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy)))));
-    }
-    {
-        const float dy = dyh, dx = fminf(dxh, fmaxf(dxl, __fmul_rn(nb_a, dy)));
-        qmin = fminf(qmin, __fmaf_rn(__fmul_rn(b, dx), dy, __fmul_rn(0.5f, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(c, dy), dy)))));
-    }
-    // the edge minimiser is exact up to rounding; shave a relative 1e-4 so that rounding can only keep, never cull
-    return __fmul_rn(qmin, 0.9999f) > q_cut;
+    const float dxn = fminf(dxh, fmaxf(dxl, 0.f)), dyn = fminf(dyh, fmaxf(dyl, 0.f));  // rectangle point nearest to the centre
+    const float qx = cut_q(a, b, c, dxn, fminf(dyh, fmaxf(dyl, __fmul_rn(nb_c, dxn))));
+    const float qy = cut_q(a, b, c, fminf(dxh, fmaxf(dxl, __fmul_rn(nb_a, dyn))), dyn);
+    // the line minimiser is exact up to rounding; shave a relative 1e-4 so that rounding can only keep, never cull
+    return __fmul_rn(fminf(qx, qy), 0.9999f) > q_cut;
 }
 
 // Warp-cooperative expansion of per-lane tile rectangles into (owner lane, tile) pairs, so that the 32 lanes of a

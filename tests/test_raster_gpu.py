@@ -255,3 +255,36 @@ def test_full_size_properties(cuda_device):
     r2 = helpers.run_ours(cam, g, cuda_device, tile_mask=mask, grads=(2 * grads[0], 2 * grads[1]))
     for k in GRADS:
         assert helpers.rel_err(r2["grads"][k], 2 * r["grads"][k]) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_tile_sharded_pieces_reassemble(cuda_device):
+    """the ranks of a tile-sharded frame render disjoint tile subsets of the same map. Emulated on one
+    GPU: the union of the pieces is bit-identical to the full render (a tile's result does not depend on which
+    other tiles are rendered) and the partial gradients add up to the full gradient."""
+    from rtg_slam_b200.parallel import TileShard
+    cam = scene.make_camera("replica")
+    g = scene.surfel_room(50_000, seed=21)
+    grads = scene.upstream_grads(cam, seed=5)
+    full = helpers.run_ours(cam, g, cuda_device, grads=grads)
+    wts = None
+    for world, weighted in ((2, False), (3, True)):
+        if weighted:  # per-tile work estimate: Gaussians whose centre falls into the tile
+            wts = torch.rand(cam.tile_grid[0] * cam.tile_grid[1], generator=torch.Generator().manual_seed(1))
+        pieces = []
+        for r in range(world):
+            sh = TileShard(cam.height, cam.width, world, r, weights=wts)
+            res = helpers.run_ours(cam, g, cuda_device, tile_mask=sh.mask.numpy(), grads=grads)
+            pieces.append((sh, res))
+        for k in ("color", "depth", "hit_color", "hit_depth", "hit_color_weight", "hit_depth_weight", "T_map"):
+            acc = np.zeros_like(full[k])
+            for sh, res in pieces:
+                pm = sh.pixel_mask.numpy()
+                acc = np.where(pm[None], res[k], acc)
+                # outside its tiles a rank holds the reference's initial values (rasterize_points.cu:79-87)
+                init = 1.0 if k == "T_map" else 0
+                assert np.all(res[k][:, ~pm] == init), k
+            assert np.array_equal(acc, full[k]), k
+        for k in full["grads"]:
+            tot = sum(res["grads"][k] for _, res in pieces)
+            assert helpers.rel_err(tot, full["grads"][k]) < 1e-4, k
