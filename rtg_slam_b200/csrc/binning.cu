@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long
     // (1) exclusive scan of the histogram -> tile offsets; (2) histogram of work classes for the launch order
     for (int base = 0; base < T; base += 1024) {
         const int i = base + tid;
-        const uint32_t c = (i < T) ? b.tile_count[i] : 0u;
+        const uint32_t c = (i < T) ? b.tile_count[(size_t)i * RTG_CNT_STRIDE] : 0u;
         local_max = max(local_max, c);
         local_act += (c > 0);
         uint32_t v = c;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long
     }
     __syncthreads();
     for (int i = tid; i < T; i += 1024) {
-        const uint32_t c = b.tile_count[i];
+        const uint32_t c = b.tile_count[(size_t)i * RTG_CNT_STRIDE];
         const int cls = (c == 0) ? 64 : 63 - (int)min(63u, c >> 6);
         b.active[atomicAdd(&s_cls[cls], 1u)] = (uint32_t)i;
     }
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
             const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
             // same (bit-identical) decision as the histogram pass in preprocess_fwd_kernel
             if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, ga.w, gb.w, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
-            const uint32_t slot = atomicAdd(b.tile_fill + t, 1u);
+            const uint32_t slot = atomicAdd(b.tile_fill + (size_t)t * RTG_CNT_STRIDE, 1u);
             const uint32_t begin = b.tile_offset[t];
             if (slot < b.tile_offset[t + 1] - begin)  // never write outside the bucket
                 b.keys[begin + slot] = ((uint64_t)s_depth[w][o] << 32) | (uint32_t)(base + o);

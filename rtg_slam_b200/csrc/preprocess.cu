@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(co
             if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, ga.w, gb.w, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1)))
                 tile_touched[tt] = 1u;
             else
-                atomicAdd(tile_count + tt, 1u);
+                atomicAdd(tile_count + (size_t)tt * RTG_CNT_STRIDE, 1u);
         }
     }
 }
