@@ -168,6 +168,33 @@ int rtg_loss_l1(const float *render, const float *depth, const int32_t *depth_in
  * > -1, zeros elsewhere; normal is (P,3). */
 int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream);
 
+/* ---- per-frame consumers of the rasterizer's index / transmittance maps ---------
+ * accumulate_gaussian_error of submodules/cuda_utils (cuda_utils.cu:17-60, map_process.cu:33-245), called by
+ * Mapping.error_gaussians_remove (SLAM/multiprocess/mapper.py:546-559): for every pixel, the colour error goes to the
+ * Gaussian named by color_index, the depth and normal errors to the one named by depth_index (indices outside [0,P)
+ * are skipped); per Gaussian the maximum (check_max) or the mean of its pixels; rescale_counter counts the pixels
+ * whose colour / depth / normal error exceeds its threshold (as a float, like the reference). All inputs (H*W), all
+ * outputs (P); outputs need not be initialised. counters: 2*P int32 of scratch, only used when !check_max. */
+int rtg_accumulate_gaussian_error(int32_t H, int32_t W, int32_t P, const float *screen_color_error, const float *screen_depth_error,
+                                  const float *screen_normal_error, const int32_t *screen_color_index,
+                                  const int32_t *screen_depth_index, float color_threshold, float depth_threshold,
+                                  float normal_threshold, int32_t check_max, float *gs_color_error, float *gs_depth_error,
+                                  float *gs_normal_error, float *gs_rescale_counter, int32_t *counters, void *stream);
+
+/* 16x16 average pooling of an (H,W) float image with zero padding, as F.avg_pool2d is used by transmission2tilemask /
+ * colorerror2tilemask (SLAM/utils.py:695-734): tile_mean (tiles_y, tiles_x) and / or tile_mask = (mean > ratio), either
+ * may be NULL. */
+int rtg_tile_mean(int32_t H, int32_t W, const float *pixels, float ratio, float *tile_mean, int32_t *tile_mask, void *stream);
+
+/* render_mask = (T_map != 1) and tile_mask = transmission2tilemask(render_mask, 16, ratio) in one pass
+ * (Mapping.evaluate_render_range, mapper.py:503-505). render_mask (H,W) bytes, may be NULL. */
+int rtg_transmission_tile_mask(int32_t H, int32_t W, const float *T_map, float ratio, uint8_t *render_mask, int32_t *tile_mask,
+                               void *stream);
+
+/* colour error image of mapper.py:481-487: sum over channels of |render - gt|, 0 where the rendered pixel is black;
+ * render, gt (3,H,W), out (H,W). */
+int rtg_color_error(int32_t H, int32_t W, const float *render, const float *gt, float *out, void *stream);
+
 /* ---- measurement hook (no reference counterpart) ---------------------------------------------
  * When enabled, every kernel launch of this library is bracketed by CUDA events on its launching stream.
  * rtg_profile_read synchronises the device and returns, per kernel id, the summed duration (ms) and the number

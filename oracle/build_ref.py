@@ -39,5 +39,28 @@ def main():
     return 0
 
 
+def build_cuda_utils():
+    """submodules/cuda_utils (accumulate_gaussian_error and friends): same recipe, module `_C`
+    kept under oracle/_ref/cuda_utils/."""
+    ref = "/root/reference/submodules/cuda_utils"
+    out = os.path.join(OUT, "cuda_utils")
+    if not os.path.isdir(ref):
+        return 0
+    if glob.glob(os.path.join(out, "_C*.so")) and "--force" not in sys.argv:
+        print("oracle/_ref/cuda_utils already built")
+        return 0
+    os.makedirs(out, exist_ok=True)
+    tmp = "/tmp/rtg_refbuild_cuda_utils"
+    shutil.rmtree(tmp, ignore_errors=True)
+    shutil.copytree(ref, tmp)
+    env = dict(os.environ, NVCC_APPEND_FLAGS="-include cstdint", TORCH_CUDA_ARCH_LIST="10.0", MAX_JOBS="8")
+    subprocess.check_call([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=tmp, env=env)
+    so = glob.glob(os.path.join(tmp, "cuda_utils", "_C*.so"))
+    assert so, "cuda_utils build produced no extension"
+    shutil.copy(so[0], out)
+    print("built", os.path.join(out, os.path.basename(so[0])))
+    return 0
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(main() or build_cuda_utils())

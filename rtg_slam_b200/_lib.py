@@ -52,6 +52,10 @@ SIGNATURES = {
     "rtg_loss_workspace_bytes": (C.c_size_t, []),
     "rtg_loss_l1": (C.c_int, [_VP] * 6 + [_I32, _I32, _I32, _F, _F, _F, _VP, _VP, _VP, _VP, _VP]),
     "rtg_normal_map": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP]),
+    "rtg_accumulate_gaussian_error": (C.c_int, [_I32, _I32, _I32] + [_VP] * 5 + [_F, _F, _F, _I32] + [_VP] * 6),
+    "rtg_tile_mean": (C.c_int, [_I32, _I32, _VP, _F, _VP, _VP, _VP]),
+    "rtg_transmission_tile_mask": (C.c_int, [_I32, _I32, _VP, _F, _VP, _VP, _VP]),
+    "rtg_color_error": (C.c_int, [_I32, _I32, _VP, _VP, _VP, _VP]),
     "rtg_profile_enable": (C.c_int, [_I32]),
     "rtg_profile_kernel_count": (C.c_int, []),
     "rtg_profile_kernel_name": (C.c_char_p, [_I32]),

@@ -325,6 +325,43 @@ int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, i
     return check_launch("rtg_normal_map");
 }
 
+int rtg_accumulate_gaussian_error(int32_t H, int32_t W, int32_t P, const float *screen_color_error, const float *screen_depth_error,
+                                  const float *screen_normal_error, const int32_t *screen_color_index,
+                                  const int32_t *screen_depth_index, float color_threshold, float depth_threshold,
+                                  float normal_threshold, int32_t check_max, float *gs_color_error, float *gs_depth_error,
+                                  float *gs_normal_error, float *gs_rescale_counter, int32_t *counters, void *stream) {
+    if (H < 0 || W < 0 || P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_accumulate_gaussian_error: negative size");
+    if (P == 0) return RTG_OK;
+    if (!gs_color_error || !gs_depth_error || !gs_normal_error || !gs_rescale_counter || (!check_max && !counters))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_accumulate_gaussian_error: NULL output");
+    if ((size_t)H * W > 0 && (!screen_color_error || !screen_depth_error || !screen_normal_error || !screen_color_index ||
+                              !screen_depth_index))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_accumulate_gaussian_error: NULL input");
+    rtg::launch_gs_error(H, W, P, screen_color_error, screen_depth_error, screen_normal_error, screen_color_index, screen_depth_index,
+                         color_threshold, depth_threshold, normal_threshold, check_max != 0, gs_color_error, gs_depth_error,
+                         gs_normal_error, gs_rescale_counter, counters, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_accumulate_gaussian_error");
+}
+
+int rtg_tile_mean(int32_t H, int32_t W, const float *pixels, float ratio, float *tile_mean, int32_t *tile_mask, void *stream) {
+    if (!pixels || H <= 0 || W <= 0 || (!tile_mean && !tile_mask)) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_tile_mean: bad arguments");
+    rtg::launch_tile_pool(H, W, pixels, 0, ratio, nullptr, tile_mean, tile_mask, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_tile_mean");
+}
+
+int rtg_transmission_tile_mask(int32_t H, int32_t W, const float *T_map, float ratio, uint8_t *render_mask, int32_t *tile_mask,
+                               void *stream) {
+    if (!T_map || !tile_mask || H <= 0 || W <= 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_transmission_tile_mask: bad arguments");
+    rtg::launch_tile_pool(H, W, T_map, 1, ratio, render_mask, nullptr, tile_mask, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_transmission_tile_mask");
+}
+
+int rtg_color_error(int32_t H, int32_t W, const float *render, const float *gt, float *out, void *stream) {
+    if (!render || !gt || !out || H <= 0 || W <= 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_color_error: bad arguments");
+    rtg::launch_color_error(H, W, render, gt, out, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_color_error");
+}
+
 int rtg_profile_enable(int32_t on) {
     std::lock_guard<std::mutex> lk(rtg::g_prof_mu);
     rtg::g_prof_on = on != 0;

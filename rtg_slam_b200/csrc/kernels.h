@@ -30,5 +30,13 @@ void launch_render_bwd(const ViewParams &vp, const GeomState &g, const BinState 
                        const float *means, const float *scales, const float *rots, const float *final_T, const int *hit_image,
                        const float *dL_dcolor, const float *dL_ddepth, float *rec, cudaStream_t s);
 
+// mapstats.cu
+void launch_gs_error(int H, int W, int P, const float *color_err, const float *depth_err, const float *normal_err,
+                     const int *color_index, const int *depth_index, float thr_c, float thr_d, float thr_n, bool check_max,
+                     float *gs_color, float *gs_depth, float *gs_normal, float *rescale, int *counters, cudaStream_t s);
+void launch_tile_pool(int H, int W, const float *pixels, int mode, float ratio, uint8_t *pixel_mask, float *tile_mean, int *tile_mask,
+                      cudaStream_t s);
+void launch_color_error(int H, int W, const float *render, const float *gt, float *err, cudaStream_t s);
+
 // adam.cu / icp.cu declared in their own sections of capi.cu
 }  // namespace rtg

@@ -139,3 +139,23 @@ def compare_outputs(a, b, tie=None, tol=1e-4, max_bad_frac=2e-4, label=""):
     frac = stats["bad_pixels"] / float(H * W)
     assert frac <= max_bad_frac, f"{label}: {stats['bad_pixels']} pixels differ beyond tol ({frac:.2e} of the image): {stats}"
     return stats
+
+
+# ---------------------------------------------------------------- map statistics
+MAPSTATS_SIZES = {"replica": (680, 1200), "ragged": (77, 45)}
+
+
+def mapstats_inputs(name):
+    """Seeded inputs of the tile-mask goldens (tests/golden/make_mapstats_golden.py regenerates them the same way): a
+    transmittance-like map (1 where nothing was rendered) and a colour-error image."""
+    H, W = MAPSTATS_SIZES[name]
+    rng = np.random.default_rng(2024 + H)
+    yy, xx = np.mgrid[0:H, 0:W]
+    T = np.ones((H, W), np.float32)
+    for _ in range(12):
+        cy, cx, r = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(5, 0.3 * min(H, W))
+        T[(yy - cy) ** 2 + (xx - cx) ** 2 < r * r] = rng.uniform(0, 0.5)
+    T[rng.uniform(size=(H, W)) < 0.02] = 0.3
+    err = (rng.uniform(size=(H, W)) ** 3).astype(np.float32)
+    err[rng.uniform(size=(H, W)) < 0.1] = 0
+    return T, err
