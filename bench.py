@@ -221,9 +221,11 @@ def main():
     _lib.profile_enable(True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]  # per-step spread (median, p10/p90)
     e0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         step()
+        marks[k].record()
     e1.record()
     barrier()
     _lib.profile_enable(False)
@@ -234,6 +236,9 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_step = float(tm.item()) / args.steps
     value = world * 1e3 / ms_step  # every rank processed one frame per step
+    per_step = np.array([(e0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(args.steps)])
+    step_ms = {"p10": float(np.percentile(per_step, 10)), "p50": float(np.percentile(per_step, 50)),
+               "p90": float(np.percentile(per_step, 90)), "note": "rank 0, same timed region as ms_per_step"}
 
     # ------------------------------------------------------------------ end to end through the public API
     rargs = types.SimpleNamespace(renderer_opaque_threshold=0.6, renderer_normal_threshold=60, renderer_depth_threshold=1.0,
@@ -371,7 +376,7 @@ def main():
                    "l2": "inputs larger than L2: 236 MB of Gaussian parameters + 84 MB of splat records + 236 MB of gradients are streamed every step (L2 = 126 MB)",
                    "visible_gaussians": vis, "num_rendered": R, "active_tiles": n_tiles, "mean_tile_list": R / max(n_tiles, 1), "max_tile_list": int(counters[3])},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline,
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "step_ms": step_ms,
     }
 
     if world > 1 and not args.no_extras:
@@ -501,6 +506,47 @@ def extras(dev, cam, t, leaves, step):
         ms = a.elapsed_time(b) / 10
         ex[f"adam_{name}_ms"] = ms
         ex[f"adam_{name}_GBps"] = 1652 * P / (ms * 1e-3) / 1e9
+    # second run with a random 50 % tile mask (the masked path of the mapper)
+    try:
+        tm = torch.from_numpy(scene.random_tile_mask(cam, 0.5, seed=7)).to(dev)
+        for _ in range(3):
+            step(tm)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(30):
+            step(tm)
+        b.record()
+        torch.cuda.synchronize()
+        ex["masked_50pct_ms_per_step"] = a.elapsed_time(b) / 30
+    except Exception as e:
+        ex["masked_50pct_ms_per_step"] = {"error": repr(e)}
+    # map statistics on the rasterizer's outputs of this frame
+    try:
+        from rtg_slam_b200 import mapstats
+        out = step()
+        H, W = out[0].shape[-2:]
+        err = mapstats.color_error_map(out[0].detach(), torch.rand_like(out[0]))
+        z = torch.zeros_like(err)
+
+        def ms_of(fn, n=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        P_ = t["xyz"].shape[0]
+        ex["accumulate_gaussian_error_ms"] = ms_of(lambda: mapstats.accumulate_gaussian_error(
+            H, W, P_, err, z, z, out[2], out[3], 0.1, 0.1, 0.1, True))
+        ex["transmission_masks_ms"] = ms_of(lambda: mapstats.transmission_masks(out[6], 0.5))
+        ex["colorerror2tilemask_ms"] = ms_of(lambda: mapstats.colorerror2tilemask(err, 16, 0.4))
+    except Exception as e:
+        ex["mapstats"] = {"error": repr(e)}
     # BASELINE configs[2]: full optimisation iteration at 1920x1080 (render + loss + backward + Adam), same map
     try:
         from rtg_slam_b200.render import Renderer
