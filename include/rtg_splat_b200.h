@@ -100,6 +100,31 @@ int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const flo
                        float *dL_dcolors_precomp, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
                        float *dL_dcov3D, float *dL_dmeans2D, void *stream);
 
+/* The same backward in two calls with the same argument list, for callers that put an exchange step between the
+ * compositing backward and the per-Gaussian backward (tile-sharded multi-GPU rendering):
+ *   rtg_splat_backward_render : zero-fill of the culled rows + backward of renderCUDA (backward.cu:808-1066); on return
+ *                               `grad2d_scratch` holds, per Gaussian, the 16-float record of partial sums
+ *                               {colour 3, mean2D 2, conic 3, opacity 1, depth-path mean 3, depth-path quaternion 4}
+ *                               over the tiles this forward rendered -- sum it across ranks (e.g. ncclAllReduce);
+ *   rtg_splat_backward_finish : computeCov2DCUDA + preprocessCUDA backward (backward.cu:273-548) from the records,
+ *                               which it clears again. Visibility (radii) does not depend on tile_mask, so ranks
+ *                               that render different tiles of one frame agree on which records exist.
+ * rtg_splat_backward == rtg_splat_backward_render followed by rtg_splat_backward_finish. */
+int rtg_splat_backward_render(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+                              const float *colors_precomp, const float *scales, const float *rotations,
+                              const float *cov3D_precomp, const int32_t *radii, const void *geom_ws, const void *img_ws,
+                              const void *bin_ws, int64_t R_cap, const int32_t *counters, const float *final_T,
+                              const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch,
+                              float *dL_dmeans3D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity,
+                              float *dL_dscales, float *dL_drotations, float *dL_dcov3D, float *dL_dmeans2D, void *stream);
+int rtg_splat_backward_finish(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+                              const float *colors_precomp, const float *scales, const float *rotations,
+                              const float *cov3D_precomp, const int32_t *radii, const void *geom_ws, const void *img_ws,
+                              const void *bin_ws, int64_t R_cap, const int32_t *counters, const float *final_T,
+                              const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch,
+                              float *dL_dmeans3D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity,
+                              float *dL_dscales, float *dL_drotations, float *dL_dcov3D, float *dL_dmeans2D, void *stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:21-26, rasterizer_impl.cu:145-157). */
 int rtg_splat_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                            uint8_t *present, void *stream);

@@ -36,12 +36,15 @@ class RtgAdamGroup(C.Structure):
 
 # name -> (restype, argtypes); must list every symbol of include/rtg_splat_b200.h
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_BWD_ARGS = [C.POINTER(RtgSplatView), _I32, _I32] + [_VP] * 6 + [_VP, _VP, _VP, _VP, _I64, _VP] + [_VP] * 4 + [_VP] + [_VP] * 8 + [_VP]
 SIGNATURES = {
     "rtg_last_error": (C.c_char_p, []),
     "rtg_version": (C.c_int, []),
     "rtg_splat_workspace_bytes": (C.c_int, [_I32, _I32, _I32, _I64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "rtg_splat_forward": (C.c_int, [C.POINTER(RtgSplatView), _I32, _I32] + [_VP] * 8 + [_VP, _VP, _VP, _I64] + [_VP] * 8 + [_VP, _VP, _VP, _VP]),
-    "rtg_splat_backward": (C.c_int, [C.POINTER(RtgSplatView), _I32, _I32] + [_VP] * 6 + [_VP, _VP, _VP, _VP, _I64, _VP] + [_VP] * 4 + [_VP] + [_VP] * 8 + [_VP]),
+    "rtg_splat_backward": (C.c_int, _BWD_ARGS),
+    "rtg_splat_backward_render": (C.c_int, _BWD_ARGS),
+    "rtg_splat_backward_finish": (C.c_int, _BWD_ARGS),
     "rtg_splat_mark_visible": (C.c_int, [_I32, _VP, _VP, _VP, _VP, _VP]),
     "rtg_adam_step": (C.c_int, [C.POINTER(RtgAdamGroup), _I32, _F, _F, _F, _I32, _VP]),
     "rtg_icp_workspace_bytes": (C.c_size_t, [_I32, _I32]),

@@ -201,7 +201,8 @@ int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const floa
     return check_launch("rtg_splat_forward");
 }
 
-int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+// phase: 0 = whole backward, 1 = zero-fill + compositing backward (fills the gradient records), 2 = per-Gaussian backward
+static int splat_backward_impl(int phase, const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
                        const float *colors_precomp, const float *scales, const float *rotations, const float *cov3D_precomp,
                        const int32_t *radii, const void *geom_ws, const void *img_ws, const void *bin_ws, int64_t R_cap,
                        const int32_t *counters, const float *final_T, const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch,
@@ -233,20 +234,39 @@ int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const flo
     // backward reads the same device counters the forward wrote.
     // fork: the zero-fill of the culled rows only depends on the forward; it streams to HBM on a side stream while
     // the compute-bound render backward runs, and joins before the call's work on `s` ends
-    SideStream *ss = side_stream();
-    cudaError_t e = ss ? cudaEventRecord(ss->fork, s) : cudaErrorUnknown;
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
-    const bool forked = (e == cudaSuccess);
-    rtg::launch_bwd_zero(P, M, shs != nullptr, cov3D_precomp == nullptr, radii, dL_dmeans3D, dL_dsh, dL_dcolors_precomp, dL_dopacity,
-                         dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, forked ? ss->stream : s);
-    if (forked) cudaEventRecord(ss->join, ss->stream);
-    rtg::launch_render_bwd(vp, g, b, img, counters, means3D, scales, rotations, final_T, hit_image, dL_dcolor, dL_ddepth,
-                           grad2d_scratch, s);
-    rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, g, b.vis_count, grad2d_scratch, dL_dmeans3D,
-                               dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, s);
-    if (forked) cudaStreamWaitEvent(s, ss->join, 0);
+    if (phase != 2) {
+        SideStream *ss = side_stream();
+        cudaError_t e = ss ? cudaEventRecord(ss->fork, s) : cudaErrorUnknown;
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
+        const bool forked = (e == cudaSuccess);
+        rtg::launch_bwd_zero(P, M, shs != nullptr, cov3D_precomp == nullptr, radii, dL_dmeans3D, dL_dsh, dL_dcolors_precomp,
+                             dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, forked ? ss->stream : s);
+        if (forked) cudaEventRecord(ss->join, ss->stream);
+        rtg::launch_render_bwd(vp, g, b, img, counters, means3D, scales, rotations, final_T, hit_image, dL_dcolor, dL_ddepth,
+                               grad2d_scratch, s);
+        if (forked) cudaStreamWaitEvent(s, ss->join, 0);  // enqueued after both: the zero-fill still overlaps render_bwd
+    }
+    if (phase != 1)
+        rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, g, b.vis_count, grad2d_scratch,
+                                   dL_dmeans3D, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,
+                                   dL_dmeans2D, s);
     return check_launch("rtg_splat_backward");
 }
+
+#define RTG_BWD_PARAMS                                                                                                             \
+    const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs, const float *colors_precomp,          \
+        const float *scales, const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom_ws,        \
+        const void *img_ws, const void *bin_ws, int64_t R_cap, const int32_t *counters, const float *final_T,                     \
+        const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch, float *dL_dmeans3D,       \
+        float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity, float *dL_dscales, float *dL_drotations, float *dL_dcov3D,  \
+        float *dL_dmeans2D, void *stream
+#define RTG_BWD_ARGS                                                                                                               \
+    view, P, M, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, geom_ws, img_ws, bin_ws, R_cap, counters,  \
+        final_T, hit_image, dL_dcolor, dL_ddepth, grad2d_scratch, dL_dmeans3D, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, \
+        dL_drotations, dL_dcov3D, dL_dmeans2D, stream
+int rtg_splat_backward(RTG_BWD_PARAMS) { return splat_backward_impl(0, RTG_BWD_ARGS); }
+int rtg_splat_backward_render(RTG_BWD_PARAMS) { return splat_backward_impl(1, RTG_BWD_ARGS); }
+int rtg_splat_backward_finish(RTG_BWD_PARAMS) { return splat_backward_impl(2, RTG_BWD_ARGS); }
 
 int rtg_splat_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,
                            void *stream) {

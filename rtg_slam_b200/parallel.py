@@ -14,7 +14,9 @@ What shards and what does not (DESIGN.md "Multi-GPU"):
   as the rasterizer's own `tile_mask` (RAST/.../__init__.py:210, forward.cu:660); every rank renders and
   back-propagates only its tiles against the replicated map, the image pieces are disjoint (`TileShard.gather`
   reassembles them when the full image is needed; the loss can stay shard-wise) and the per-Gaussian gradients are
-  partial sums that the same flat all-reduce completes;
+  partial sums, completed either by the same flat all-reduce (236 B / Gaussian) or -- `TileShard.exchange_records` --
+  by summing the 64-byte gradient records between the two halves of the backward (rtg_splat_backward_render /
+  _finish), after which every rank computes the identical full gradient itself;
 * ICP is a 27-number reduction per iteration at <= 0.8 Mpx: replicas only, never sharded.
 """
 from __future__ import annotations
@@ -125,6 +127,27 @@ class TileShard:
             owner[t] = r
             load[r] += float(wt[t])
         return owner
+
+    def exchange_records(self):
+        """Context manager: while active, every rasterizer backward sums its (P, 16) gradient records over the ranks
+        (one all-reduce of 64 B per Gaussian, between the compositing backward and the per-Gaussian backward) instead of
+        leaving partial dense gradients to be all-reduced afterwards (236 B per Gaussian). All ranks then compute the
+        identical, complete gradient; no further collective is needed before the replicated optimizer step."""
+        import contextlib
+
+        from . import rasterizer
+
+        @contextlib.contextmanager
+        def cm():
+            def hook(rec):
+                if self.world > 1:
+                    dist.all_reduce(rec, op=dist.ReduceOp.SUM)
+            prev = rasterizer.set_grad_record_hook(hook)
+            try:
+                yield self
+            finally:
+                rasterizer.set_grad_record_hook(prev)
+        return cm()
 
     def gather(self, img: torch.Tensor, fill: float = 0.0) -> torch.Tensor:
         """Full image from the ranks' disjoint pieces: pixels a rank does not own are replaced by zero, one SUM

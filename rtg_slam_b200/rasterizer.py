@@ -263,14 +263,34 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp is not None else None
         scratch = st.get_scratch(P)
         if P > 0:
-            check(L.rtg_splat_backward(
-                C.byref(view), P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp),
-                _ptr(radii), _ptr(saved.geom), _ptr(saved.img), _ptr(saved.bin), saved.r_cap, _ptr(saved.counters),
-                _ptr(T_map), _ptr(hit_depth), _ptr(grad_out_color), _ptr(grad_out_depth), _ptr(scratch),
-                _ptr(g_means), _ptr(g_sh), _ptr(g_colors), _ptr(g_opac), _ptr(g_scales), _ptr(g_rot), _ptr(g_cov), None,
-                C.c_void_p(stream)), "rtg_splat_backward")
+            args = (C.byref(view), P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales), _ptr(rotations),
+                    _ptr(cov3Ds_precomp), _ptr(radii), _ptr(saved.geom), _ptr(saved.img), _ptr(saved.bin), saved.r_cap,
+                    _ptr(saved.counters), _ptr(T_map), _ptr(hit_depth), _ptr(grad_out_color), _ptr(grad_out_depth), _ptr(scratch),
+                    _ptr(g_means), _ptr(g_sh), _ptr(g_colors), _ptr(g_opac), _ptr(g_scales), _ptr(g_rot), _ptr(g_cov), None,
+                    C.c_void_p(stream))
+            hook = _GRAD_RECORD_HOOK[0]
+            if hook is None:
+                check(L.rtg_splat_backward(*args), "rtg_splat_backward")
+            else:
+                # exchange step between the compositing backward and the per-Gaussian backward (tile-sharded frames)
+                check(L.rtg_splat_backward_render(*args), "rtg_splat_backward_render")
+                hook(scratch[:P * 16].view(P, 16))
+                check(L.rtg_splat_backward_finish(*args), "rtg_splat_backward_finish")
         # same order as the forward's arguments (reference __init__.py:269-279)
         return g_means, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, None, None
+
+
+# Optional exchange step of the backward: a callable that receives the (P, 16) fp32 gradient-record tensor after the
+# compositing backward and must leave the summed records in place (e.g. `dist.all_reduce`). Set by
+# parallel.TileShard.exchange_records(); None = single call, no exchange.
+_GRAD_RECORD_HOOK = [None]
+
+
+def set_grad_record_hook(fn):
+    """Install (or, with None, remove) the backward's exchange step; returns the previous hook."""
+    prev = _GRAD_RECORD_HOOK[0]
+    _GRAD_RECORD_HOOK[0] = fn
+    return prev
 
 
 def rasterize_gaussians(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask, raster_settings):

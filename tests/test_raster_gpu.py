@@ -288,3 +288,45 @@ def test_tile_sharded_pieces_reassemble(cuda_device):
         for k in full["grads"]:
             tot = sum(res["grads"][k] for _, res in pieces)
             assert helpers.rel_err(tot, full["grads"][k]) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_two_phase_backward_with_record_exchange(cuda_device):
+    """rtg_splat_backward_render / _finish with an exchange step in between (TileShard.exchange_records). Emulated on
+    one GPU: pass 1 captures every shard's gradient records, pass 2 substitutes their sum -- the gradients that come out
+    are those of the full frame; without a hook the two-phase path is the one-call path."""
+    from rtg_slam_b200 import rasterizer
+    from rtg_slam_b200.parallel import TileShard
+    cam = scene.make_camera("replica")
+    g = scene.surfel_room(40_000, seed=22)
+    grads = scene.upstream_grads(cam, seed=5)
+    full = helpers.run_ours(cam, g, cuda_device, grads=grads)
+    world = 3
+    shards = [TileShard(cam.height, cam.width, world, r) for r in range(world)]
+    captured = []
+
+    def capture(rec):
+        captured.append(rec.clone())
+    prev = rasterizer.set_grad_record_hook(capture)
+    try:
+        for sh in shards:
+            helpers.run_ours(cam, g, cuda_device, tile_mask=sh.mask.numpy(), grads=grads)
+        assert len(captured) == world and captured[0].shape == (40_000, 16)
+        total = sum(captured)
+        assert float(total.abs().max()) > 0
+
+        def substitute(rec):
+            rec.copy_(total)
+        rasterizer.set_grad_record_hook(substitute)
+        res = helpers.run_ours(cam, g, cuda_device, tile_mask=shards[1].mask.numpy(), grads=grads)
+        for k in full["grads"]:
+            assert helpers.rel_err(res["grads"][k], full["grads"][k]) < 1e-4, k
+        # identity exchange == single call (records are consumed and cleared either way)
+        rasterizer.set_grad_record_hook(lambda rec: None)
+        same = helpers.run_ours(cam, g, cuda_device, grads=grads)
+    finally:
+        rasterizer.set_grad_record_hook(prev)
+    again = helpers.run_ours(cam, g, cuda_device, grads=grads)
+    for k in full["grads"]:
+        assert helpers.rel_err(same["grads"][k], full["grads"][k]) < 1e-5, k
+        assert helpers.rel_err(again["grads"][k], full["grads"][k]) < 1e-5, k   # scratch left clean
