@@ -106,12 +106,17 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
         return;
     }
 
-    const float2 pixf = make_float2((float)px, (float)py);
+    // A pixel that is finished (or outside the image) moves infinitely far away: every later entry then fails the
+    // `power >= -q_cut` test (power = -inf or NaN), so the visit loop needs no separate `done` branch.
+    const float FAR = 1e30f;
+    float pfx = inside ? (float)px : FAR;
+    const float pfy = (float)py;
     const float3 ray = pixel_ray(px, py, vp.focal_x, vp.focal_y, vp.cx, vp.cy);
     const float tx0 = (float)((tile % vp.tiles_x) * RTG_TILE), ty0 = (float)((tile / vp.tiles_x) * RTG_TILE);
     const uint32_t a_s0 = smem_addr(s_s0), a_s1 = smem_addr(s_s1), a_rgb = smem_addr(s_rgb), a_id = smem_addr(s_id),
                    a_mask = smem_addr(s_mask);
-    const float opaque_thr = vp.opaque_thr, T_thr = vp.T_thr;
+    const float T_thr = vp.T_thr;
+    float opaque_thr = vp.opaque_thr;  // becomes +inf once the pixel has its opaque hit: `!hit &&` folded into the compare
     bool done = !inside;
 
     float T = 1.0f, end_T = 1.0f;
@@ -149,6 +154,9 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
         const int cnt = min(BATCH, n - i * BATCH);
         if (__all_sync(FULL, done)) continue;  // warp-uniform
         const int chunks = (cnt + 31) >> 5;
+        // batch-local bookkeeping, resolved once per batch instead of once per blend: slot of the last colour
+        // contribution and of the current arg-max weight (-1 = none in this batch)
+        int j_last = -1, j_cmax = -1;
         for (int c = 0; c < chunks; c++) {
             const int e = (c << 5) + lane;
             const uint32_t mm = (e < cnt) ? lds32(a_mask + (boff + e) * 4) : 0u;
@@ -157,46 +165,43 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                 const int j = (c << 5) + __ffs(bits) - 1;
                 const uint32_t jb = boff + (uint32_t)j;
                 bits &= bits - 1;
-                if (!done) {
-                    const float4 s0 = lds128(a_s0 + jb * 16), s1 = lds128(a_s1 + jb * 16);
-                    const float dx = s0.x - pixf.x, dy = s0.y - pixf.y;
-                    const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
-                    // power > 0: skipped by the reference; power < -q_cut: alpha is certainly below 1/255
-                    if (power <= 0.0f && power >= -s0.z) {
-                        const float alpha = fminf(0.99f, s1.w * expf(power));
-                        if (alpha >= 1.0f / 255.0f) {
-                            if (!hit && alpha >= opaque_thr) {
-                                const int id = (int)lds32(a_id + jb * 4);
-                                depth_ = surfel_depth(__ldg(g.hit + 2 * (size_t)id), __ldg(g.hit + 2 * (size_t)id + 1), ray, s0.w,
-                                                      vp.depth_thr, vp.normal_thr);
-                                hit_id = id;
-                                hit_dw = alpha * T;
-                                hit = true;
-                            }
-                            const float test_T = T * (1.f - alpha);
-                            if (test_T < T_thr) {
-                                // no colour is added any more; the pixel keeps scanning until it has an opaque hit
-                                if (hit) done = true;
-                                else T = test_T;
-                            } else {
-                                const float cw = alpha * T;
-                                const float4 col = lds128(a_rgb + jb * 16);
-                                C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
-                                if (cw > cw_max) {
-                                    cw_max = cw;
-                                    hit_color_id = (int)lds32(a_id + jb * 4);
-                                    hit_cw = cw;
-                                }
-                                last_contributor = (uint32_t)(i * BATCH + j + 1);
-                                end_T = test_T;
-                                T = test_T;
-                            }
+                const float4 s0 = lds128(a_s0 + jb * 16), s1 = lds128(a_s1 + jb * 16);
+                const float dx = s0.x - pfx, dy = s0.y - pfy;
+                const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
+                // power > 0: skipped by the reference; power < -q_cut: alpha is certainly below 1/255; finished pixel: never
+                if (power <= 0.0f && power >= -s0.z) {
+                    const float alpha = fminf(0.99f, s1.w * expf(power));
+                    if (alpha >= 1.0f / 255.0f) {
+                        if (alpha >= opaque_thr) {  // first opaque entry only (opaque_thr = +inf afterwards)
+                            const int id = (int)lds32(a_id + jb * 4);
+                            depth_ = surfel_depth(__ldg(g.hit + 2 * (size_t)id), __ldg(g.hit + 2 * (size_t)id + 1), ray, s0.w,
+                                                  vp.depth_thr, vp.normal_thr);
+                            hit_id = id;
+                            hit_dw = alpha * T;
+                            hit = true;
+                            opaque_thr = __int_as_float(0x7f800000);
+                        }
+                        const float test_T = T * (1.f - alpha);
+                        if (test_T < T_thr) {
+                            // no colour is added any more; the pixel keeps scanning until it has an opaque hit
+                            if (hit) { done = true; pfx = FAR; }
+                            else T = test_T;
+                        } else {
+                            const float cw = alpha * T;
+                            const float4 col = lds128(a_rgb + jb * 16);
+                            C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
+                            if (cw > cw_max) { cw_max = cw; hit_cw = cw; j_cmax = j; }
+                            j_last = j;
+                            end_T = test_T;
+                            T = test_T;
                         }
                     }
                 }
             }
             if (__all_sync(FULL, done)) break;  // checked once per 32 entries: a finished warp skips visits cheaply
         }
+        if (j_last >= 0) last_contributor = (uint32_t)(i * BATCH + j_last + 1);
+        if (j_cmax >= 0) hit_color_id = (int)lds32(a_id + (boff + (uint32_t)j_cmax) * 4);
     }
 
     if (inside) {
