@@ -193,6 +193,21 @@ int rtg_loss_l1(const float *render, const float *depth, const int32_t *depth_in
  * > -1, zeros elsewhere; normal is (P,3). */
 int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream);
 
+/* ---- tracker-side preprocessing of an incoming depth frame --------------------------
+ * Tracker.map_preprocess (SLAM/multiprocess/tracker.py:97-132): optional bilateral depth filter (bilateralFilter_torch,
+ * SLAM/utils.py:550-589; taps with i^2+j^2 <= radius^2, zero padding, zero-depth neighbours ignored), valid-range mask
+ * (min_depth, max_depth) exclusive, vertex map and Sobel normal map (compute_vertex_map / compute_normal_map,
+ * SLAM/utils.py:65-122), confidence = |cos(normal, pixel ray)| (compute_confidence_map, SLAM/utils.py:125-138), and the
+ * invalid-confidence masking: where the normal is zero or the confidence is below the threshold, depth, vertex, normal
+ * and confidence are set to 0 and invalid_mask_out (may be NULL) to 1. depth_in / depth_out (H,W); vertex, normal
+ * (H,W,3) channels-last; confidence (H,W). depth_in == depth_out is allowed only without the filter. With vertex_out,
+ * normal_out, confidence_out and invalid_mask_out all NULL only the filter and the range mask run.
+ * ws: rtg_icp_workspace_bytes() bytes. */
+int rtg_frame_preprocess(const float *depth_in, int32_t H, int32_t W, int32_t depth_filter, int32_t radius, float sigma_color,
+                         float sigma_space, float min_depth, float max_depth, float fx, float fy, float cx, float cy,
+                         float invalid_confidence_thresh, float *depth_out, float *vertex_out, float *normal_out,
+                         float *confidence_out, uint8_t *invalid_mask_out, void *ws, void *stream);
+
 /* ---- per-frame consumers of the rasterizer's index / transmittance maps ---------
  * accumulate_gaussian_error of submodules/cuda_utils (cuda_utils.cu:17-60, map_process.cu:33-245), called by
  * Mapping.error_gaussians_remove (SLAM/multiprocess/mapper.py:546-559): for every pixel, the colour error goes to the

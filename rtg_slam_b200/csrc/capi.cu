@@ -345,6 +345,22 @@ int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, i
     return check_launch("rtg_normal_map");
 }
 
+int rtg_frame_preprocess(const float *depth_in, int32_t H, int32_t W, int32_t depth_filter, int32_t radius, float sigma_color,
+                         float sigma_space, float min_depth, float max_depth, float fx, float fy, float cx, float cy,
+                         float invalid_confidence_thresh, float *depth_out, float *vertex_out, float *normal_out,
+                         float *confidence_out, uint8_t *invalid_mask_out, void *ws, void *stream) {
+    const bool maps = vertex_out || normal_out || confidence_out || invalid_mask_out;
+    if (!depth_in || !depth_out || H <= 0 || W <= 0 || (maps && (!vertex_out || !normal_out || !confidence_out || !ws)))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_frame_preprocess: bad arguments");
+    if (depth_filter && (radius < 0 || radius > 15 || !(sigma_color > 0.f) || !(sigma_space > 0.f)))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_frame_preprocess: bad filter parameters");
+    if (depth_in == depth_out && depth_filter) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_frame_preprocess: the filter is not in-place");
+    rtg::launch_frame_preprocess(depth_in, H, W, depth_filter, radius, sigma_color, sigma_space, min_depth, max_depth, fx, fy, cx, cy,
+                                 invalid_confidence_thresh, depth_out, vertex_out, normal_out, confidence_out, invalid_mask_out, ws,
+                                 reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_frame_preprocess");
+}
+
 int rtg_accumulate_gaussian_error(int32_t H, int32_t W, int32_t P, const float *screen_color_error, const float *screen_depth_error,
                                   const float *screen_normal_error, const int32_t *screen_color_index,
                                   const int32_t *screen_depth_index, float color_threshold, float depth_threshold,

@@ -38,5 +38,11 @@ void launch_tile_pool(int H, int W, const float *pixels, int mode, float ratio, 
                       cudaStream_t s);
 void launch_color_error(int H, int W, const float *render, const float *gt, float *err, cudaStream_t s);
 
+// frameprep.cu
+void launch_frame_preprocess(const float *depth_in, int H, int W, int filter, int radius, float sigma_color, float sigma_space,
+                             float min_depth, float max_depth, float fx, float fy, float cx, float cy, float conf_thresh,
+                             float *depth_out, float *vertex, float *normal, float *confidence, uint8_t *invalid, void *ws,
+                             cudaStream_t s);
+
 // adam.cu / icp.cu declared in their own sections of capi.cu
 }  // namespace rtg

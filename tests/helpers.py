@@ -159,3 +159,26 @@ def mapstats_inputs(name):
     err = (rng.uniform(size=(H, W)) ** 3).astype(np.float32)
     err[rng.uniform(size=(H, W)) < 0.1] = 0
     return T, err
+
+
+# ---------------------------------------------------------------- tracker-side frame preprocessing
+FRAMEPREP_CASES = {
+    # thresholds of configs/tum (invalid_confidence_thresh 0.5) and configs/replica (0.2); depth range of base.yaml
+    "tum": dict(cam="small", depth_filter=True, min_depth=0.3, max_depth=5.0, thresh=0.5),
+    "nofilter_ragged": dict(cam="ragged", depth_filter=False, min_depth=0.5, max_depth=4.0, thresh=0.2),
+}
+
+
+def frameprep_inputs(name):
+    """A noisy ray-cast depth image of the box room with holes (zero depth), as a depth sensor delivers it."""
+    from rtg_slam_b200 import scene
+    cfg = FRAMEPREP_CASES[name]
+    cam = scene.make_camera(cfg["cam"])
+    rng = np.random.default_rng(77 + cam.width)
+    depth = scene.raycast_room_depth(cam).astype(np.float32)
+    depth = depth + rng.normal(0, 0.004, depth.shape).astype(np.float32)
+    holes = rng.uniform(size=depth.shape) < 0.03
+    depth[holes] = 0
+    depth[: cam.height // 6, : cam.width // 5] = 0          # a larger missing region
+    K = [[cam.fx, 0.0, cam.cx], [0.0, cam.fy, cam.cy], [0.0, 0.0, 1.0]]
+    return np.ascontiguousarray(depth, dtype=np.float32), K
