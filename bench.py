@@ -380,11 +380,17 @@ def main():
     }
 
     if world > 1 and not args.no_extras:
-        dp = dp_optimize(args, dev, world, leaves, step, barrier)
-        ts = dp_optimize(args, dev, world, leaves, step, barrier, tile_shard=(H, W))
-        tr = dp_optimize(args, dev, world, leaves, step, barrier, tile_shard=(H, W), records=True)
+        # side measurements of the multi-GPU modes with an exchange step (every rank takes the same path, so a
+        # failure is symmetric and cannot strand the other ranks in a collective)
+        ex = {}
+        for name, kw in (("dp_optimize", {}), ("tile_sharded_optimize", {"tile_shard": (H, W)}),
+                         ("tile_sharded_records_optimize", {"tile_shard": (H, W), "records": True})):
+            try:
+                ex[name] = dp_optimize(args, dev, world, leaves, step, barrier, **kw)
+            except Exception as e:  # the headline line must still be printed
+                ex[name] = {"error": repr(e)}
         if rank == 0:
-            line["extras"] = {"dp_optimize": dp, "tile_sharded_optimize": ts, "tile_sharded_records_optimize": tr}
+            line["extras"] = ex
     if rank == 0 and world == 1 and not args.no_extras:
         line["cpu_baseline"] = cpu_baseline(args, cam)
         line["extras"] = extras(dev, cam, t, leaves, step)
