@@ -57,6 +57,26 @@ def test_adam_rejects_bad_groups():
     assert L.rtg_adam_step(arr, 1, 0.9, 0.999, 1e-15, 0, None) == -1  # step must be >= 1
 
 
+def test_side_entry_points_validate_before_touching_cuda():
+    """The widened rows (SURVEY 8(f) #1-#3) and the two-call backward reject bad arguments on the host."""
+    L = _lib.lib()
+    nul = [None]
+    assert L.rtg_accumulate_gaussian_error(-1, 4, 4, *(nul * 5), 0.1, 0.1, 0.1, 1, *(nul * 6)) == -1
+    assert L.rtg_accumulate_gaussian_error(4, 4, 0, *(nul * 5), 0.1, 0.1, 0.1, 1, *(nul * 6)) == 0      # P == 0: nothing to do
+    assert L.rtg_accumulate_gaussian_error(4, 4, 3, *(nul * 5), 0.1, 0.1, 0.1, 1, *(nul * 6)) == -1
+    assert b"NULL output" in L.rtg_last_error()
+    assert L.rtg_tile_mean(16, 16, None, 0.5, None, None, None) == -1
+    assert L.rtg_transmission_tile_mask(0, 16, None, 0.5, None, None, None) == -1
+    assert L.rtg_color_error(16, 16, None, None, None, None) == -1
+    assert L.rtg_frame_preprocess(None, 16, 16, 1, 5, 2.0, 2.0, 0.3, 5.0, 1.0, 1.0, 0.0, 0.0, 0.2, *(nul * 7)) == -1
+    assert b"rtg_frame_preprocess" in L.rtg_last_error()
+    assert L.rtg_loss_l1(*(nul * 6), 16, 16, 0, 0.8, 1.0, 0.1, *(nul * 5)) == -1
+    assert L.rtg_normal_map(None, None, 16, 16, None, None) == -1
+    for fn in (L.rtg_splat_backward, L.rtg_splat_backward_render, L.rtg_splat_backward_finish):
+        assert fn(None, 1, 16, *(nul * 6), *(nul * 4), 0, None, *(nul * 4), None, *(nul * 8), None) == -1
+        assert b"view is NULL" in L.rtg_last_error()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
