@@ -460,9 +460,7 @@ def dp_optimize(args, dev, world, leaves, step, barrier, tile_shard=None, record
 def rast_counters(dev):
     """num_rendered / active tiles of the last forward (pinned copy written by the scan kernel)."""
     from rtg_slam_b200 import rasterizer
-    st = rasterizer._state(dev)
-    pinned, ev = st.pinned[-1]
-    return [int(x) for x in pinned[:4]]
+    return [int(x) for x in rasterizer.last_counters(dev)]
 
 
 def cpu_baseline(args, cam):

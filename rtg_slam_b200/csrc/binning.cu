@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
     const float2 nb = cut_slopes(s1.x, s1.y, s1.z);
     s_ga[w][lane] = make_float4(s0.x, s0.y, s0.z, nb.x);  // x, y, q_cut, -b/c
     s_gb[w][lane] = make_float4(s1.x, s1.y, s1.z, nb.y);  // conic, -b/a
-    s_depth[w][lane] = __float_as_uint(s0.w);
+    s_depth[w][lane] = (r > 0) ? __float_as_uint(g.hit[2 * (size_t)idx + 1].z) : 0u;  // view depth (forward.cu:336, rasterizer_impl.cu:96)
     __syncwarp();
     const int base = idx - lane;
     for (int k = lane; k < total; k += 32) {

@@ -12,7 +12,10 @@ namespace rtg {
 
 // Gradient record slots (one 64-byte line per Gaussian, filled by render-backward atomics,
 // consumed and cleared by preprocess-backward).
-enum { REC_COLOR = 0, REC_MEAN2D = 3, REC_CONIC = 5, REC_OPACITY = 8, REC_DMEAN = 9, REC_DROT = 12 };
+// Slots 3..8 hold the six moments  sum u, u dx, u dy, u dx^2, u dx dy, u dy^2  of u = (opacity * G) * dL/dalpha over the
+// blended (pixel, Gaussian) pairs (d = centre - pixel): every 2-D gradient of backward.cu:926-995 is a fixed linear
+// combination of them (moments_to_grad2d), formed once per Gaussian by the per-Gaussian backward pass.
+enum { REC_COLOR = 0, REC_M0 = 3, REC_MX = 4, REC_MY = 5, REC_MXX = 6, REC_MXY = 7, REC_MYY = 8, REC_DMEAN = 9, REC_DROT = 12 };
 
 struct ViewParams {
     int H, W, tiles_x, tiles_y;
@@ -25,11 +28,11 @@ struct ViewParams {
 // Per-Gaussian state written by the forward preprocess (16-byte records so that every gather in the render
 // kernels is one LDG.128; the two halves of `splat` share a 32-byte sector).
 struct GeomState {
-    float4 *splat;     // [2P]  [2i]   = pixel-space centre (x, y), q_cut, view-space depth
-                       //       [2i+1] = inverse 2-D covariance (a, b, c), opacity
+    float4 *splat;     // [2P]  [2i]   = pixel-space centre (x, y), q_cut, opacity
+                       //       [2i+1] = inverse 2-D covariance (a, b, c), log2(opacity)
     float4 *rgb_flags; // [P]   SH colour (clamped at 0) + clamp bits (int in .w)
     float4 *hit;       // [2P]  [2i]   = view-space normal (xyz), scale_max*scale_modifier
-                       //       [2i+1] = view-space centre (xyz), normal axis (int in .w)
+                       //       [2i+1] = view-space centre (xyz; z = the view depth of the sort key), normal axis (int in .w)
     uint32_t *vis_list; // [P]  ids of the Gaussians that survived the preprocess (count in BinState::vis_count)
 };
 
@@ -182,6 +185,53 @@ __device__ __forceinline__ bool rect_below_cutoff(float gx, float gy, float a, f
     const float qy = cut_q(a, b, c, fminf(dxh, fmaxf(dxl, __fmul_rn(nb_a, dyn))), dyn);
     // the line minimiser is exact up to rounding; shave a relative 1e-4 so that rounding can only keep, never cull
     return __fmul_rn(fminf(qx, qy), 0.9999f) > q_cut;
+}
+
+// ------------------------------------------------------------------ alpha of a (pixel, Gaussian) pair
+// The reference evaluates  alpha = min(0.99, opacity * expf(power))  with the accurate expf (forward.cu:764-771,
+// backward.cu:940-945). Here the fast path is one FFMA and one MUFU.EX2:  au = 2^(power*log2(e) + log2(opacity)),
+// relative error <= 1e-6 (half an ulp of an exponent of magnitude <= 8 twice, plus the 2^-22 of ex2.approx). The only
+// discontinuous decision taken on alpha for every pair is `alpha < 1/255`: when the fast value lands within RTG_ALPHA_BAND
+// (relative, 4x the error bound) of that threshold the reference expression is evaluated instead, so the decision is the
+// reference's. Forward and backward call the same function on the same inputs: they agree bit for bit on which pairs
+// blend and with what alpha. `au` is the unclamped opacity * G (the backward's moments are sums of au * dL/dalpha).
+#define RTG_ALPHA_BAND 4e-6f
+#define RTG_LOG2E 1.4426950408889634f
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// the reference's exponent, same expression in every kernel (forward.cu:757, backward.cu:936)
+__device__ __forceinline__ float pair_power(float a, float b, float c, float dx, float dy) {
+    return -0.5f * (a * dx * dx + c * dy * dy) - b * dx * dy;
+}
+// returns false if the pair is skipped (alpha < 1/255)
+__device__ __forceinline__ bool pair_alpha(float power, float log2o, float opacity, float &alpha, float &au) {
+    au = ex2_approx(fmaf(power, RTG_LOG2E, log2o));
+    alpha = fminf(0.99f, au);
+    if (alpha < (1.0f / 255.0f) * (1.0f - RTG_ALPHA_BAND)) return false;
+    if (alpha < (1.0f / 255.0f) * (1.0f + RTG_ALPHA_BAND)) {  // a few pairs per frame
+        au = opacity * expf(power);
+        alpha = fminf(0.99f, au);
+        return alpha >= 1.0f / 255.0f;
+    }
+    return true;
+}
+
+// The same function split in two for callers that evaluate several pairs per step without a branch in between:
+// pair_alpha_fast never branches; when it reports `band` the caller must run pair_alpha_exact on that pair.
+__device__ __forceinline__ bool pair_alpha_fast(float power, float log2o, float &alpha, float &au, bool &band) {
+    au = ex2_approx(fmaf(power, RTG_LOG2E, log2o));
+    alpha = fminf(0.99f, au);
+    band = alpha < (1.0f / 255.0f) * (1.0f + RTG_ALPHA_BAND);
+    return alpha >= (1.0f / 255.0f) * (1.0f - RTG_ALPHA_BAND);
+}
+static __device__ __noinline__ float pair_au_exact(float power, float opacity) { return opacity * expf(power); }  // out of line: rare
+__device__ __forceinline__ bool pair_alpha_exact(float power, float opacity, float &alpha, float &au) {
+    au = pair_au_exact(power, opacity);
+    alpha = fminf(0.99f, au);
+    return alpha >= 1.0f / 255.0f;
 }
 
 // Warp-cooperative expansion of per-lane tile rectangles into (owner lane, tile) pairs, so that the 32 lanes of a

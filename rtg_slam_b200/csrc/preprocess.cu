@@ -227,8 +227,8 @@ __device__ __forceinline__ bool preprocess_one(const ViewParams &vp, const int i
     const float opacity = __ldg(opac + idx);
     const float q_cut = q_cutoff(opacity);
     radii[idx] = (int)my_radius;
-    g.splat[2 * (size_t)idx] = make_float4(pix.x, pix.y, q_cut, pv.z);
-    g.splat[2 * (size_t)idx + 1] = make_float4(conic.x, conic.y, conic.z, opacity);
+    g.splat[2 * (size_t)idx] = make_float4(pix.x, pix.y, q_cut, opacity);
+    g.splat[2 * (size_t)idx + 1] = make_float4(conic.x, conic.y, conic.z, log2f(opacity));  // see pair_alpha (common.cuh)
     g.rgb_flags[idx] = make_float4(rgb.x, rgb.y, rgb.z, __int_as_float(flags));
     g.hit[2 * (size_t)idx] = h0;
     g.hit[2 * (size_t)idx + 1] = h1;
@@ -456,9 +456,17 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
     float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)idx * RTG_REC);
     const float4 ra = r4[0], rb = r4[1], rc = r4[2], rd = r4[3];  // cleared at the very end, see below
     const float dcol[3] = {ra.x, ra.y, ra.z};
-    const float g2x = ra.w, g2y = rb.x;
-    const float dcon[3] = {rb.y, rb.z, rb.w};  // conic.x, conic.y, conic.w
-    const float dopac = rc.x;
+    // The compositing backward leaves the six moments of u = opacity*G*dL/dalpha (common.cuh, REC_M*). With
+    // dL/dG = opacity*dL/dalpha, d = centre - pixel and the conic (a, b, c), backward.cu:960-995 reads
+    //   dL/dmean2D.x = sum dL/dG * (-G dx a - G dy b) * W/2 = -(a Mx + b My) * W/2      (.y: -(c My + b Mx) * H/2)
+    //   dL/dconic.{x,y,w} = sum -0.5 G d{x,x,y} d{x,y,y} dL/dG = -0.5 * {Mxx, Mxy, Myy}
+    //   dL/dopacity = sum G dL/dalpha = M0 / opacity
+    const float4 sp0 = g.splat[2 * (size_t)idx], sp1 = g.splat[2 * (size_t)idx + 1];
+    const float m0 = ra.w, mx = rb.x, my = rb.y, mxx = rb.z, mxy = rb.w, myy = rc.x;
+    const float g2x = -(sp1.x * mx + sp1.y * my) * (0.5f * (float)vp.W);
+    const float g2y = -(sp1.z * my + sp1.y * mx) * (0.5f * (float)vp.H);
+    const float dcon[3] = {-0.5f * mxx, -0.5f * mxy, -0.5f * myy};  // conic.x, conic.y, conic.w
+    const float dopac = m0 / sp0.w;
     float3 dmean = make_float3(rc.y, rc.z, rc.w);  // depth path
     float4 drot = rd;                              // depth path
 

@@ -8,15 +8,20 @@
 //    staged into shared memory, the staging thread also computes, once per entry, which of the 8 patches the
 //    Gaussian can reach above the alpha cut-off (exact convex minimisation, common.cuh). Each warp then walks
 //    only its own entries (ballot + find-first-set), so entries that every lane would skip are never visited;
-//  * per pair, the exponential is evaluated only if -power <= ln(255*opacity) + margin, i.e. only when the
-//    reference's `alpha < 1/255` test could pass;
+//  * per pair, alpha comes from one FFMA + one MUFU.EX2 (pair_alpha, common.cuh); the reference's accurate
+//    expression is evaluated only when that value is within 4e-6 (relative) of the 1/255 cut, and for the one entry
+//    per pixel that decides the opaque hit when it is that close to opaque_threshold;
 //  * the plane hit is evaluated lazily, only for the first entry with alpha >= opaque_threshold, from a
 //    per-Gaussian view-space record (the reference recomputes quaternion->normal and two 4x3 transforms from
 //    global memory for every blended pair, forward.cu:778-790);
-//  * the backward walks only the prefix of the tile list that some pixel of the CTA actually blended, reduces
-//    the 9 per-pair gradient terms across the warp with a transposing butterfly (16 shuffles instead of 45) and
-//    issues one 9-lane atomic per (warp, Gaussian) into a 64-byte gradient record, instead of 9 atomics per
-//    (pixel, Gaussian) pair;
+//  * the backward walks only the prefix of the tile list that some pixel of the CTA actually blended. Per pair it
+//    accumulates three colour terms and six moments of u = opacity*G*dL/dalpha (sum u, u dx, u dy, u dx^2, u dx dy,
+//    u dy^2): all 2-D gradients of backward.cu:960-995 are linear in them, so the per-pair work is 9 multiply-adds
+//    and the conversion happens once per Gaussian in the per-Gaussian pass. The colour behind a pair enters only
+//    through its dot product with dL/dC, so the replay keeps one scalar instead of three channels. The two pixels of a
+//    lane are blended without a branch (a skipped pair is a pair with alpha = 0, which leaves the replay state
+//    bit-identical). The 9 sums are reduced across the warp with a transposing butterfly (12 shuffles instead of 45)
+//    and added with one 9-lane atomic per (warp, Gaussian), instead of 9 atomics per (pixel, Gaussian) pair;
 //  * hit_normal_c / hit_point_c are not stored per pixel: they are functions of the hit Gaussian and the pixel
 //    ray and are recomputed bit-identically in the backward.
 #include "common.cuh"
@@ -27,6 +32,14 @@ namespace rtg {
 
 #define BATCH 256
 #define FULL 0xffffffffu
+
+// power > 0 is skipped by the reference. (A second cheap rejection, power < -q_cut, was measured slower than letting
+// the one-instruction exponential decide: render_bwd 0.404 -> 0.392 ms.)
+#ifdef RTG_QCUT_PRETEST
+#define RTG_FWD_PRETEST(power, q_cut) ((power) <= 0.0f && (power) >= -(q_cut))
+#else
+#define RTG_FWD_PRETEST(power, q_cut) ((power) <= 0.0f)
+#endif
 
 // warp w of the CTA owns the 8x4 patch (w & 1, w >> 1) of the 16x16 tile
 __device__ __forceinline__ void pixel_of(const ViewParams &vp, int tile, int &px, int &py, bool &inside) {
@@ -118,7 +131,9 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
 #define REC_S1(k) (a_rec + (k) * 48 + 16)
 #define REC_RGB(k) (a_rec + (k) * 48 + 32)
     const float T_thr = vp.T_thr;
-    float opaque_thr = vp.opaque_thr;  // becomes +inf once the pixel has its opaque hit: `!hit &&` folded into the compare
+    // lower edge of the band around opaque_threshold; becomes +inf once the pixel has its opaque hit (`!hit &&` folded
+    // into the compare)
+    float opaque_lo = vp.opaque_thr * (1.0f - RTG_ALPHA_BAND);
     bool done = !inside;
 
     float T = 1.0f, end_T = 1.0f;
@@ -127,7 +142,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
     float depth_ = 0.f;
     bool hit = false;
     int hit_id = -1, hit_color_id = -1;
-    float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
+    float cw_max = -1.f, hit_dw = 0.f;  // arg-max colour weight (forward.cu:725-726: max starts at -1, the output at 0)
 
     const int rounds = (n + BATCH - 1) / BATCH;
     // stage(batch, id): asynchronous gather of one list entry per thread into buffer (batch & 1)
@@ -169,34 +184,36 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                 bits &= bits - 1;
                 const float4 s0 = lds128(REC_S0(jb)), s1 = lds128(REC_S1(jb));
                 const float dx = s0.x - pfx, dy = s0.y - pfy;
-                const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
-                // power > 0: skipped by the reference; power < -q_cut: alpha is certainly below 1/255; finished pixel: never
-                if (power <= 0.0f && power >= -s0.z) {
-                    const float alpha = fminf(0.99f, s1.w * expf(power));
-                    if (alpha >= 1.0f / 255.0f) {
-                        if (alpha >= opaque_thr) {  // first opaque entry only (opaque_thr = +inf afterwards)
+                const float power = pair_power(s1.x, s1.y, s1.z, dx, dy);
+                // power > 0: skipped by the reference; finished pixel: power = -inf or NaN, never passes
+                float alpha, au;
+                if (RTG_FWD_PRETEST(power, s0.z) && pair_alpha(power, s1.w, s0.w, alpha, au)) {
+                    if (alpha >= opaque_lo) {  // at most a few entries per pixel (opaque_lo = +inf after the hit)
+                        // inside the band the decision is taken on the reference's own expression
+                        const float a_dec = (alpha < vp.opaque_thr * (1.0f + RTG_ALPHA_BAND)) ? fminf(0.99f, s0.w * expf(power)) : alpha;
+                        if (a_dec >= vp.opaque_thr) {
                             const int id = (int)lds32(a_id + jb * 4);
-                            depth_ = surfel_depth(__ldg(g.hit + 2 * (size_t)id), __ldg(g.hit + 2 * (size_t)id + 1), ray, s0.w,
-                                                  vp.depth_thr, vp.normal_thr);
+                            const float4 h0 = __ldg(g.hit + 2 * (size_t)id), h1 = __ldg(g.hit + 2 * (size_t)id + 1);
+                            depth_ = surfel_depth(h0, h1, ray, h1.z, vp.depth_thr, vp.normal_thr);
                             hit_id = id;
                             hit_dw = alpha * T;
                             hit = true;
-                            opaque_thr = __int_as_float(0x7f800000);
+                            opaque_lo = __int_as_float(0x7f800000);
                         }
-                        const float test_T = T * (1.f - alpha);
-                        if (test_T < T_thr) {
-                            // no colour is added any more; the pixel keeps scanning until it has an opaque hit
-                            if (hit) { done = true; pfx = FAR; }
-                            else T = test_T;
-                        } else {
-                            const float cw = alpha * T;
-                            const float4 col = lds128(REC_RGB(jb));
-                            C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
-                            if (cw > cw_max) { cw_max = cw; hit_cw = cw; j_cmax = j; }
-                            j_last = j;
-                            end_T = test_T;
-                            T = test_T;
-                        }
+                    }
+                    const float test_T = T * (1.f - alpha);
+                    if (test_T < T_thr) {
+                        // no colour is added any more; the pixel keeps scanning until it has an opaque hit
+                        if (hit) { done = true; pfx = FAR; }
+                        else T = test_T;
+                    } else {
+                        const float cw = alpha * T;
+                        const float4 col = lds128(REC_RGB(jb));
+                        C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
+                        if (cw > cw_max) { cw_max = cw; j_cmax = j; }
+                        j_last = j;
+                        end_T = test_T;
+                        T = test_T;
                     }
                 }
             }
@@ -214,7 +231,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
         out_depth[pix_id] = depth_;
         out_hit_depth[pix_id] = hit_id;
         out_hit_color[pix_id] = hit_color_id;
-        out_hcw[pix_id] = hit_cw;
+        out_hcw[pix_id] = fmaxf(cw_max, 0.f);
         out_hdw[pix_id] = hit_dw;
         out_T[pix_id] = end_T;
         img.n_contrib[pix_id] = last_contributor;
@@ -363,57 +380,50 @@ __device__ __forceinline__ void depth_hit_grad(const ViewParams &vp, const GeomS
     }
 }
 
-// Per-pixel replay state of the backward (one pixel): everything the reference keeps in registers between entries.
+// Per-pixel replay state of the backward. The reference keeps, per channel, the colour accumulated behind the current
+// entry (accum_rec) and the previous entry's colour (backward.cu:947-958); both enter dL/dalpha only through their dot
+// product with the pixel's dL/dC, so one scalar each is kept: A = accum_rec . dLp,  L = last_color . dLp.
 struct BwdPix {
-    float T, T_final, accum0, accum1, accum2, last_alpha, lc0, lc1, lc2, dLp0, dLp1, dLp2, bg_dot, pyf;
+    float T, A, L, last_alpha, dLp0, dLp1, dLp2, bgw, pyf;
     uint32_t last_contributor;
 };
 
-// One (pixel, Gaussian) pair of the back-to-front replay (backward.cu:926-995); adds the 9 gradient terms to v[].
-__device__ __forceinline__ bool bwd_pair(BwdPix &p, const uint32_t pos, const float4 s0, const float4 s1, const float dx,
-                                         const uint32_t a_rgb_j, const float ddelx_dx, const float ddely_dy, float v[9]) {
-    if (!(pos < p.last_contributor)) return false;
-    const float dy = s0.y - p.pyf;
-    const float power = -0.5f * (s1.x * dx * dx + s1.z * dy * dy) - s1.y * dx * dy;
-    if (!((power <= 0.0f) && (power >= -s0.z))) return false;  // skipped by the reference / certainly below 1/255
-    const float G = expf(power);
-    const float alpha = fminf(0.99f, s1.w * G);
-    if (alpha < 1.0f / 255.0f) return false;
-    float inv_1ma;  // 1 - alpha is in [0.01, 0.996]: the bare MUFU.RCP (no range fix-up code) is exact to 1 ulp there
+// One (pixel, Gaussian) pair of the back-to-front replay (backward.cu:926-995), branch-free: a pair that does not blend
+// is passed with alpha = au = 0, which leaves T (x 1/(1-0)), A (the recurrence's next step multiplies L by last_alpha = 0)
+// and every sum bit-identical to skipping it. Adds the three colour terms and the six moments to v[].
+__device__ __forceinline__ void bwd_blend(BwdPix &p, const float alpha, const float au, const float4 col, const float dx,
+                                          const float dy, float v[9]) {
+    float inv_1ma;  // 1 - alpha is in [0.01, 1]: the bare MUFU.RCP (no range fix-up code) is exact to 1 ulp there
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
     p.T = p.T * inv_1ma;
-    const float dch = alpha * p.T;
-    const float4 col = lds128(a_rgb_j);
-    p.accum0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.accum0; p.lc0 = col.x;
-    p.accum1 = p.last_alpha * p.lc1 + (1.f - p.last_alpha) * p.accum1; p.lc1 = col.y;
-    p.accum2 = p.last_alpha * p.lc2 + (1.f - p.last_alpha) * p.accum2; p.lc2 = col.z;
-    float dL_dalpha = (col.x - p.accum0) * p.dLp0;
-    dL_dalpha += (col.y - p.accum1) * p.dLp1;
-    dL_dalpha += (col.z - p.accum2) * p.dLp2;
-    v[REC_COLOR + 0] += dch * p.dLp0;
-    v[REC_COLOR + 1] += dch * p.dLp1;
-    v[REC_COLOR + 2] += dch * p.dLp2;
-    dL_dalpha *= p.T;
+    const float w = alpha * p.T;
+    const float D = col.x * p.dLp0 + col.y * p.dLp1 + col.z * p.dLp2;
+    p.A = fmaf(p.last_alpha, p.L - p.A, p.A);  // accum_rec = last_alpha * last_color + (1 - last_alpha) * accum_rec
+    p.L = D;
     p.last_alpha = alpha;
-    if (p.bg_dot != 0.f) dL_dalpha += (-p.T_final * inv_1ma) * p.bg_dot;
-    const float dL_dG = s1.w * dL_dalpha;
-    const float gdx = G * dx, gdy = G * dy;
-    const float dG_ddelx = -gdx * s1.x - gdy * s1.y;
-    const float dG_ddely = -gdy * s1.z - gdx * s1.y;
-    v[REC_MEAN2D + 0] += dL_dG * dG_ddelx * ddelx_dx;
-    v[REC_MEAN2D + 1] += dL_dG * dG_ddely * ddely_dy;
-    v[REC_CONIC + 0] += -0.5f * gdx * dx * dL_dG;
-    v[REC_CONIC + 1] += -0.5f * gdx * dy * dL_dG;
-    v[REC_CONIC + 2] += -0.5f * gdy * dy * dL_dG;
-    v[REC_OPACITY] += G * dL_dalpha;
-    return true;
+    float dL_dalpha = (D - p.A) * p.T;
+    dL_dalpha = fmaf(-p.bgw, inv_1ma, dL_dalpha);  // background term, bgw = T_final * (bg . dLp)  (backward.cu:976-981)
+    v[REC_COLOR + 0] = fmaf(w, p.dLp0, v[REC_COLOR + 0]);
+    v[REC_COLOR + 1] = fmaf(w, p.dLp1, v[REC_COLOR + 1]);
+    v[REC_COLOR + 2] = fmaf(w, p.dLp2, v[REC_COLOR + 2]);
+    const float u = au * dL_dalpha;
+    const float ux = u * dx, uy = u * dy;
+    v[REC_M0] += u;
+    v[REC_MX] += ux;
+    v[REC_MY] += uy;
+    v[REC_MXX] = fmaf(ux, dx, v[REC_MXX]);
+    v[REC_MXY] = fmaf(ux, dy, v[REC_MXY]);
+    v[REC_MYY] = fmaf(uy, dy, v[REC_MYY]);
 }
 
 // Backward compositing. 128 threads per tile; a warp owns an 8x8 pixel patch and every lane two vertically adjacent
 // pixels, so the per-entry costs that do not depend on the pixel (list walk, shared-memory fetch of the splat, the
 // warp reduction and the atomic) are paid once per 64 pixels.
 #define BWD_THREADS 128
-__global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b,
+#ifndef BWD_MIN_BLOCKS
+#define BWD_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(BWD_THREADS, BWD_MIN_BLOCKS) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b,
                                                                const ImgState img, const int *__restrict__ counters,
                                                                const float *__restrict__ means, const float *__restrict__ scales,
                                                                const float *__restrict__ rots, const float *__restrict__ final_T,
@@ -425,6 +435,10 @@ __global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParam
     __shared__ int s_id[BATCH];
     __shared__ uint32_t s_mask[BATCH];
     __shared__ uint32_t s_max[4];
+#ifdef RTG_BWD_SMEM_REDUCE
+    __shared__ float4 s_red[4][9 * 8];
+    const uint32_t a_red = smem_addr(s_red[threadIdx.x >> 5]);
+#endif
 
     if (counters[2]) return;
     if ((int)blockIdx.x >= counters[1]) return;  // empty tiles sit at the end of the launch order
@@ -444,22 +458,21 @@ __global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParam
     const float tx0 = (float)(tx * RTG_TILE), ty0 = (float)(ty * RTG_TILE);
     const uint32_t a_s0 = smem_addr(s_s0), a_s1 = smem_addr(s_s1), a_rgb = smem_addr(s_rgb), a_id = smem_addr(s_id),
                    a_mask = smem_addr(s_mask);
-    const float bg0 = __ldg(vp.bg), bg1 = __ldg(vp.bg + 1), bg2 = __ldg(vp.bg + 2);
 
     BwdPix A, B;
     {
-        A.T_final = insA ? final_T[pidA] : 0.f; B.T_final = insB ? final_T[pidB] : 0.f;
-        A.T = A.T_final; B.T = B.T_final;
+        const float bg0 = __ldg(vp.bg), bg1 = __ldg(vp.bg + 1), bg2 = __ldg(vp.bg + 2);
+        A.T = insA ? final_T[pidA] : 0.f; B.T = insB ? final_T[pidB] : 0.f;
         A.last_contributor = insA ? img.n_contrib[pidA] : 0u; B.last_contributor = insB ? img.n_contrib[pidB] : 0u;
         A.dLp0 = insA ? dL_dcolor[pidA] : 0.f; A.dLp1 = insA ? dL_dcolor[N + pidA] : 0.f; A.dLp2 = insA ? dL_dcolor[2 * N + pidA] : 0.f;
         B.dLp0 = insB ? dL_dcolor[pidB] : 0.f; B.dLp1 = insB ? dL_dcolor[N + pidB] : 0.f; B.dLp2 = insB ? dL_dcolor[2 * N + pidB] : 0.f;
-        A.bg_dot = bg0 * A.dLp0 + bg1 * A.dLp1 + bg2 * A.dLp2; B.bg_dot = bg0 * B.dLp0 + bg1 * B.dLp1 + bg2 * B.dLp2;
+        A.bgw = A.T * (bg0 * A.dLp0 + bg1 * A.dLp1 + bg2 * A.dLp2); B.bgw = B.T * (bg0 * B.dLp0 + bg1 * B.dLp1 + bg2 * B.dLp2);
         // a pixel whose upstream colour gradient is exactly zero (outside the render mask of the mapping loss) adds
         // exact zeros to every colour-path term: skip its replay altogether
         if (A.dLp0 == 0.f && A.dLp1 == 0.f && A.dLp2 == 0.f) A.last_contributor = 0u;
         if (B.dLp0 == 0.f && B.dLp1 == 0.f && B.dLp2 == 0.f) B.last_contributor = 0u;
-        A.accum0 = A.accum1 = A.accum2 = A.last_alpha = A.lc0 = A.lc1 = A.lc2 = 0.f;
-        B.accum0 = B.accum1 = B.accum2 = B.last_alpha = B.lc0 = B.lc1 = B.lc2 = 0.f;
+        A.A = A.L = A.last_alpha = 0.f;
+        B.A = B.L = B.last_alpha = 0.f;
         A.pyf = (float)pyA; B.pyf = (float)pyB;
     }
 
@@ -472,7 +485,6 @@ __global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParam
     const uint32_t m = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
 
     const int my_slot = (lane & 1) ? -1 : reduce9_slot(lane);  // lanes 2k and 2k+1 hold the same total: one of them adds it
-    const float ddelx_dx = 0.5f * vp.W, ddely_dy = 0.5f * vp.H;
 
     const int rounds = ((int)m + BATCH - 1) / BATCH;
     for (int i = 0; i < rounds; i++) {
@@ -510,16 +522,51 @@ __global__ void __launch_bounds__(BWD_THREADS) render_bwd_kernel(const ViewParam
                 const int j = (c << 5) + __ffs(bits) - 1;
                 bits &= bits - 1;
                 const uint32_t pos = m - 1 - (uint32_t)(i * BATCH + j);
+                const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
+                const float dx = s0.x - pxf, dyA = s0.y - A.pyf, dyB = s0.y - B.pyf;
+                const float pwA = pair_power(s1.x, s1.y, s1.z, dx, dyA), pwB = pair_power(s1.x, s1.y, s1.z, dx, dyB);
+                float alA, auA, alB, auB;
+                // same decisions as the forward: same power expression, same pretest, same alpha function
+#ifdef RTG_BWD_BRANCHY_ALPHA
+                const bool okA = pos < A.last_contributor && RTG_FWD_PRETEST(pwA, s0.z) && pair_alpha(pwA, s1.w, s0.w, alA, auA);
+                const bool okB = pos < B.last_contributor && RTG_FWD_PRETEST(pwB, s0.z) && pair_alpha(pwB, s1.w, s0.w, alB, auB);
+#else
+                bool bandA, bandB;
+                bool okA = pair_alpha_fast(pwA, s1.w, alA, auA, bandA) && pos < A.last_contributor && RTG_FWD_PRETEST(pwA, s0.z);
+                bool okB = pair_alpha_fast(pwB, s1.w, alB, auB, bandB) && pos < B.last_contributor && RTG_FWD_PRETEST(pwB, s0.z);
+                bandA = bandA && okA; bandB = bandB && okB;
+                if (bandA || bandB) {  // a few pairs per frame
+                    if (bandA) okA = pair_alpha_exact(pwA, s0.w, alA, auA);
+                    if (bandB) okB = pair_alpha_exact(pwB, s0.w, alB, auB);
+                }
+#endif
+                if (!__any_sync(FULL, okA || okB)) continue;
+                const float4 col = lds128(a_rgb + j * 16);
                 float v[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) v[k] = 0.f;
-                const float4 s0 = lds128(a_s0 + j * 16), s1 = lds128(a_s1 + j * 16);
-                const float dx = s0.x - pxf;
-                const bool actA = bwd_pair(A, pos, s0, s1, dx, a_rgb + j * 16, ddelx_dx, ddely_dy, v);
-                const bool actB = bwd_pair(B, pos, s0, s1, dx, a_rgb + j * 16, ddelx_dx, ddely_dy, v);
-                if (!__any_sync(FULL, actA || actB)) continue;
+                bwd_blend(A, okA ? alA : 0.f, okA ? auA : 0.f, col, dx, dyA, v);
+                bwd_blend(B, okB ? alB : 0.f, okB ? auB : 0.f, col, dx, dyB, v);
+#ifdef RTG_BWD_SMEM_REDUCE
+                // transposition through a warp-private [9][32] shared array: lane L < 18 sums 16 lanes of value L >> 1
+                // (four 128-bit loads), lane pairs combine, even lanes add the total
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 9; k++) sts32(a_red + (uint32_t)(k * 32 + lane) * 4, __float_as_uint(v[k]));
+                __syncwarp();
+                float tot = 0.f;
+                if (lane < 18) {
+                    const uint32_t a = a_red + (uint32_t)((lane >> 1) * 32 + (lane & 1) * 16) * 4;
+                    const float4 q0 = lds128(a), q1 = lds128(a + 16), q2 = lds128(a + 32), q3 = lds128(a + 48);
+                    tot = ((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w)) +
+                          (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));
+                }
+                tot += __shfl_xor_sync(FULL, tot, 1);
+                if (lane < 18 && !(lane & 1)) atomicAdd(rec + (size_t)lds32(a_id + j * 4) * RTG_REC + (lane >> 1), tot);
+#else
                 const float tot = warp_reduce9(v, lane);
                 if (my_slot >= 0) atomicAdd(rec + (size_t)lds32(a_id + j * 4) * RTG_REC + my_slot, tot);
+#endif
             }
         }
     }

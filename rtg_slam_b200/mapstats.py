@@ -87,13 +87,14 @@ def pixelmask2tilemask(pixelmask, stride):
 
 
 def colorerror2tilemask(color_error, stride, top_ratio=0.4):
-    """(H,W) float error -> float (tiles_y, tiles_x) mask of the int(numel * top_ratio) tiles with the largest mean
-    error (torch.topk on the pooled map, as in the reference; the pooling is the native pass)."""
+    """(H,W) float error -> int32 (tiles_y, tiles_x) mask of the int(numel * top_ratio) tiles with the largest mean
+    error (torch.topk on the pooled map, as in the reference; the pooling is the native pass). int32 like the
+    reference's devI(...) (SLAM/utils.py:733-735): the mapper hands it to Renderer.render as tile_mask."""
     _tile_grid(color_error.shape[0], color_error.shape[1], stride)
     mean, _ = _tile_mean(color_error, 0.0, True, False)
     k = int(mean.numel() * top_ratio)
     _, top = torch.topk(mean.view(-1), k=k)
-    mask = torch.zeros_like(mean)
+    mask = torch.zeros(mean.shape, dtype=torch.int32, device=mean.device)
     mask.view(-1)[top] = 1
     return mask
 

@@ -5,10 +5,12 @@ Mirrors `diff_gaussian_rasterization_depth/__init__.py` of the reference (RAST/.
 exactly-one-of checks, same 8-tuple of outputs, same gradient tuple. What is different underneath:
 
 * the native side is a C ABI called through ctypes with raw pointers and the current stream;
-* no blocking read-backs: the instance count stays on the device. The binning buffer is sized from the
-  previous call; the scan kernel drops the counters into pinned host memory and the shim waits only for
-  that kernel (the rest of the forward keeps running) to detect the rare overflow, in which case the
-  forward is re-run with a larger buffer;
+* no blocking read-backs on the steady path: the instance count stays on the device. The binning buffer is
+  sized from earlier calls (1.5x the largest instance count seen); the scan kernel drops the counters into
+  pinned host memory. The first call of a (P, H, W) shape waits for that kernel (the rest of the forward keeps
+  running) and re-runs the forward with a larger buffer on overflow; later calls do not wait at all -- their
+  counters are read when they have arrived (at the next call, and at the latest at the call's own backward), and
+  an overflow, which left that frame empty, raises instead of passing silently (`set_capacity_checks`);
 * outputs and gradients are `torch.empty` -- the kernels write every element (the reference fills 9
   tensors with `torch::full` / `zeros` first).
 """
@@ -47,6 +49,15 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 # ----------------------------------------------------------------------------- per-device state
+class _Pending:
+    """Counters of one forward call that have not been read yet: pinned buffer + the event recorded after the scan kernel."""
+    __slots__ = ("pinned", "event", "r_cap", "done", "num_rendered", "overflow")
+
+    def __init__(self, pinned, event, r_cap):
+        self.pinned, self.event, self.r_cap = pinned, event, r_cap
+        self.done, self.num_rendered, self.overflow = False, 0, False
+
+
 class _DeviceState:
     """Capacity hint for the binning buffer, pinned counters, gradient scratch; one per CUDA device."""
 
@@ -55,12 +66,15 @@ class _DeviceState:
         self.r_hint = 1 << 16
         self.scratch = None  # (P*16,) zeros, cleared by the backward kernel itself
         self.ones_masks = {}
-        self.pinned = []  # free list of (pinned tensor, event)
-        self.sync_checks = True
+        self.free = []      # free list of (pinned tensor, event): only buffers whose event has completed
+        self.pending = []   # _Pending of calls whose counters have not been read yet, oldest first
+        self.mode = "auto"  # "sync" | "auto" | "deferred"
+        self.seen = set()   # (P, H, W) shapes whose capacity has been measured by a waiting call
+        self.last = (0, 0, 0, 0)  # counters of the most recent call that has been read
 
     def get_pinned(self):
-        if self.pinned:
-            return self.pinned.pop()
+        if self.free:
+            return self.free.pop()
         t = torch.zeros(_lib.RTG_CNT_WORDS, dtype=torch.int32).pin_memory()
         ev = torch.cuda.Event()
         with torch.cuda.device(self.device):
@@ -69,8 +83,36 @@ class _DeviceState:
             raise RuntimeError("could not create a CUDA event for the capacity check")
         return t, ev
 
-    def put_pinned(self, item):
-        self.pinned.append(item)
+    def read(self, p: _Pending, block: bool) -> bool:
+        """Reads the counters of call `p` if its scan kernel has finished (or waits for it). True if read."""
+        if p.done:
+            return True
+        if block:
+            p.event.synchronize()
+        elif not p.event.query():
+            return False
+        p.num_rendered, p.overflow = int(p.pinned[0]), bool(int(p.pinned[2]))
+        self.last = tuple(int(x) for x in p.pinned[:4])
+        p.done = True
+        # 1.5x head room: the steady path does not wait for the count of the current frame
+        self.r_hint = max(self.r_hint, int(p.num_rendered * 1.5) + 4096)
+        self.free.append((p.pinned, p.event))  # the event has completed: the buffer may be reused
+        p.pinned = p.event = None
+        if p in self.pending:
+            self.pending.remove(p)
+        return True
+
+    def reap(self, block: bool = False):
+        """Reads every outstanding call's counters that has arrived; raises if one of them overflowed unnoticed."""
+        bad = None
+        for p in list(self.pending):
+            if self.read(p, block) and p.overflow:
+                bad = p
+        if bad is not None:
+            raise RuntimeError(
+                f"rasterizer: an earlier forward needed {bad.num_rendered} (Gaussian, tile) instances but its binning buffer "
+                f"held {bad.r_cap}; that frame was rendered empty. The capacity has been raised -- render the frame again, "
+                "or call set_capacity_checks('sync') to have every forward wait for its own count.")
 
     def get_scratch(self, P):
         n = P * 16
@@ -95,11 +137,30 @@ def _state(device) -> _DeviceState:
     return _STATES[idx]
 
 
-def set_async_capacity_checks(enabled: bool, device=None) -> None:
-    """enabled=False: never wait for the scan kernel; an overflow is then only detected at the next call
-    (the frame that overflowed renders as empty). Default True."""
+def set_capacity_checks(mode: str, device=None) -> None:
+    """How a forward learns whether its binning buffer was large enough (the instance count is only known on the device):
+    'sync'     every forward waits for its scan kernel (not for the rest of the forward) and re-runs on overflow;
+    'auto'     (default) the first forward of a (P, H, W) shape does that; later ones do not wait -- the buffer holds 1.5x
+               the largest count seen, their counters are read once they have arrived, and an overflow (which leaves that
+               frame empty) raises RuntimeError at the next rasterizer call or at the frame's own backward;
+    'deferred' like 'auto' without the waiting first call."""
+    if mode not in ("sync", "auto", "deferred"):
+        raise ValueError("mode must be 'sync', 'auto' or 'deferred'")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    _state(dev).sync_checks = bool(enabled)
+    _state(dev).mode = mode
+
+
+def set_async_capacity_checks(enabled: bool, device=None) -> None:
+    """Round-1 name: True = 'sync' (wait for the scan kernel in every forward), False = 'deferred'."""
+    set_capacity_checks("sync" if enabled else "deferred", device)
+
+
+def last_counters(device=None):
+    """(num_rendered, active tiles, overflow, longest tile list) of the most recent forward on `device` (waits for it)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    st = _state(dev)
+    st.reap(block=True)
+    return st.last
 
 
 def _ptr(t):
@@ -138,7 +199,7 @@ def _make_view(rs: GaussianRasterizationSettings, device) -> tuple[RtgSplatView,
 
 class _Saved:
     """State kept between forward and backward (the reference keeps geomBuffer / binningBuffer / imgBuffer)."""
-    __slots__ = ("geom", "img", "bin", "r_cap", "counters", "view_keep")
+    __slots__ = ("ws", "geom", "img", "bin", "r_cap", "counters", "view_keep", "pending")
 
 
 def _forward_native(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask):
@@ -182,30 +243,34 @@ def _forward_native(rs, means3D, sh, colors_precomp, opacities, scales, rotation
     gb, ib, bb = C.c_size_t(), C.c_size_t(), C.c_size_t()
     saved = _Saved()
     saved.view_keep = keep
+    st.reap()  # counters of earlier calls that have arrived meanwhile (raises on an unnoticed overflow)
+    shape_key = (P, H, W)
+    wait = st.mode == "sync" or (st.mode == "auto" and shape_key not in st.seen)
     r_cap = int(st.r_hint)
     while True:
         check(L.rtg_splat_workspace_bytes(P, H, W, r_cap, C.byref(gb), C.byref(ib), C.byref(bb)), "rtg_splat_workspace_bytes")
-        saved.geom = torch.empty(gb.value, dtype=torch.uint8, device=device)
-        saved.img = torch.empty(ib.value, dtype=torch.uint8, device=device)
-        saved.bin = torch.empty(bb.value, dtype=torch.uint8, device=device)
-        saved.counters = torch.empty(_lib.RTG_CNT_WORDS, **i32)
+        # one allocation for the three workspaces and the device counters (256-byte aligned pieces)
+        ws = torch.empty(gb.value + ib.value + bb.value + 256, dtype=torch.uint8, device=device)
+        base = ws.data_ptr()
+        saved.ws = ws
+        saved.geom, saved.img, saved.bin = base, base + gb.value, base + gb.value + ib.value
+        saved.counters = base + gb.value + ib.value + bb.value
         saved.r_cap = r_cap
         pinned, event = st.get_pinned()
         check(L.rtg_splat_forward(
             C.byref(view), P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
-            _ptr(cov3Ds_precomp), _ptr(tile_mask), _ptr(saved.geom), _ptr(saved.img), _ptr(saved.bin), r_cap,
+            _ptr(cov3Ds_precomp), _ptr(tile_mask), C.c_void_p(saved.geom), C.c_void_p(saved.img), C.c_void_p(saved.bin), r_cap,
             _ptr(color), _ptr(depth), _ptr(hit_color), _ptr(hit_depth), _ptr(hit_cw), _ptr(hit_dw), _ptr(T_map), _ptr(radii),
-            _ptr(saved.counters), C.c_void_p(pinned.data_ptr()), C.c_void_p(event.cuda_event), C.c_void_p(stream)),
+            C.c_void_p(saved.counters), C.c_void_p(pinned.data_ptr()), C.c_void_p(event.cuda_event), C.c_void_p(stream)),
             "rtg_splat_forward")
-        if not st.sync_checks:
-            # deferred: use whatever the previous call reported (event may not have fired yet)
-            st.put_pinned((pinned, event))
+        pend = _Pending(pinned, event, r_cap)
+        saved.pending = pend
+        if not wait:
+            st.pending.append(pend)  # read at the next call / at this call's backward
             break
-        event.synchronize()  # waits for the scan kernel only; scatter / sort / render are still running
-        num_rendered, overflow = int(pinned[0]), int(pinned[2])
-        st.put_pinned((pinned, event))
-        st.r_hint = max(st.r_hint, int(num_rendered * 1.25) + 4096)
-        if not overflow:
+        st.read(pend, block=True)  # waits for the scan kernel only; scatter / sort / render are still running
+        if not pend.overflow:
+            st.seen.add(shape_key)
             break
         r_cap = int(st.r_hint)
     return (color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii), saved, (means3D, sh, colors_precomp, scales, rotations,
@@ -262,10 +327,16 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_rot = torch.empty((P, 4), **f32) if rotations is not None else None
         g_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp is not None else None
         scratch = st.get_scratch(P)
+        if not saved.pending.done:  # a forward that did not wait for its count: it has arrived by now
+            st.read(saved.pending, block=True)
+        if saved.pending.overflow:
+            raise RuntimeError(f"rasterizer: this frame needed {saved.pending.num_rendered} (Gaussian, tile) instances but its "
+                               f"binning buffer held {saved.pending.r_cap}; it was rendered empty. The capacity has been raised: "
+                               "render it again (set_capacity_checks('sync') makes every forward check its own count).")
         if P > 0:
             args = (C.byref(view), P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales), _ptr(rotations),
-                    _ptr(cov3Ds_precomp), _ptr(radii), _ptr(saved.geom), _ptr(saved.img), _ptr(saved.bin), saved.r_cap,
-                    _ptr(saved.counters), _ptr(T_map), _ptr(hit_depth), _ptr(grad_out_color), _ptr(grad_out_depth), _ptr(scratch),
+                    _ptr(cov3Ds_precomp), _ptr(radii), C.c_void_p(saved.geom), C.c_void_p(saved.img), C.c_void_p(saved.bin), saved.r_cap,
+                    C.c_void_p(saved.counters), _ptr(T_map), _ptr(hit_depth), _ptr(grad_out_color), _ptr(grad_out_depth), _ptr(scratch),
                     _ptr(g_means), _ptr(g_sh), _ptr(g_colors), _ptr(g_opac), _ptr(g_scales), _ptr(g_rot), _ptr(g_cov), None,
                     C.c_void_p(stream))
             hook = _GRAD_RECORD_HOOK[0]

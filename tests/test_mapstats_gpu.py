@@ -105,3 +105,12 @@ def test_color_error_map_on_a_render(cuda_device):
     # end to end: the mapper's global-optimisation mask from a render (mapper.py:481-499)
     tm = mapstats.colorerror2tilemask(ours, 16, 0.3)
     assert tm.shape == cam.tile_grid and int(tm.sum()) == int(tm.numel() * 0.3)
+    # ... which the mapper passes straight to Renderer.render as tile_mask (mapper.py:500-506): int32, accepted as is
+    assert tm.dtype == torch.int32
+    masked = helpers.run_ours(cam, g, cuda_device, tile_mask=tm.cpu().numpy())
+    from rtg_slam_b200.rasterizer import GaussianRasterizer
+    rs = helpers.make_settings(cam, cuda_device)
+    t = helpers.to_torch(g, cuda_device)
+    out = GaussianRasterizer(rs)(means3D=t["xyz"], opacities=t["opacity"], shs=t["shs"], scales=t["scales"],
+                                 rotations=t["rotations"], tile_mask=tm)
+    assert np.array_equal(out[0].cpu().numpy(), masked["color"])

@@ -62,17 +62,25 @@ def test_matches_reference_cuda_golden(cuda_device, name):
         assert helpers.rel_err(ours["grads"][k], gold["grad_" + k]) < tol, k
 
 
-@pytest.mark.parametrize("camname,P", [("tum", 10000), ("replica", 60000)])
-def test_matches_live_reference_cuda(cuda_device, camname, P):
+# (camera, Gaussians, tile-mask keep fraction). The last four are the timed configurations: BASELINE.json configs[1]
+# (~300 k @1200x680), the headline scene of bench.py (1 M @1200x680: its longest tile list exceeds the 4096-key
+# on-chip sort, i.e. the chunked-merge path), the same with a 50 % tile mask, and configs[2] (1 M @1920x1080).
+LIVE_CASES = [("tum", 10_000, None), ("replica", 60_000, None), ("replica", 300_000, None), ("replica", 1_000_000, None),
+              ("replica", 1_000_000, 0.5), ("hd", 1_000_000, None)]
+
+
+@pytest.mark.parametrize("camname,P,keep", LIVE_CASES)
+def test_matches_live_reference_cuda(cuda_device, camname, P, keep):
     if helpers.ref_cuda_module() is None:
         pytest.skip("oracle/_ref not built")
     cam = scene.make_camera(camname)
     g = scene.surfel_room(P, seed=2024)
+    mask = None if keep is None else scene.random_tile_mask(cam, keep, seed=11)
     grads = scene.upstream_grads(cam, seed=5)
-    ours = helpers.run_ours(cam, g, cuda_device, grads=grads)
-    ref = helpers.run_ref_cuda(cam, g, cuda_device, grads=grads)
-    ref2 = helpers.run_ref_cuda(cam, g, cuda_device, grads=grads)
-    st = helpers.compare_outputs(ours, ref, tol=1e-4, max_bad_frac=5e-4, label=camname)
+    ours = helpers.run_ours(cam, g, cuda_device, tile_mask=mask, grads=grads)
+    ref = helpers.run_ref_cuda(cam, g, cuda_device, tile_mask=mask, grads=grads)
+    ref2 = helpers.run_ref_cuda(cam, g, cuda_device, tile_mask=mask, grads=grads)
+    st = helpers.compare_outputs(ours, ref, tol=1e-4, max_bad_frac=5e-4, label=f"{camname}/{P}/{keep}")
     assert st["radii_mismatch"] == 0
     for k in GRADS:
         jitter = helpers.rel_err(ref2["grads"][k], ref["grads"][k])
@@ -183,11 +191,41 @@ def test_capacity_overflow_is_retried(cuda_device):
     cam = scene.make_camera("small")
     g = scene.surfel_room(3000, seed=1)
     st = rasterizer._state(cuda_device)
-    st.r_hint = 16  # far too small: the first attempt must overflow and be re-run
-    ours = helpers.run_ours(cam, g, cuda_device)
     o = OracleRender(cam, g, precision="f32", tie_eps=1e-4)
-    helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, label="overflow retry")
-    assert st.r_hint >= o.num_rendered
+    st.reap(block=True)
+    try:
+        # a forward that waits for its own count ('sync', and the first call of a shape in 'auto') re-runs on overflow
+        rasterizer.set_capacity_checks("sync", cuda_device)
+        st.r_hint = 16  # far too small: the first attempt must overflow and be re-run
+        ours = helpers.run_ours(cam, g, cuda_device)
+        helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, label="overflow retry")
+        assert st.r_hint >= o.num_rendered
+        rasterizer.set_capacity_checks("auto", cuda_device)
+        st.seen.clear()
+        st.r_hint = 16
+        ours = helpers.run_ours(cam, g, cuda_device)  # first call of this shape: waits, retries
+        helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, label="overflow retry (auto, first call)")
+        # a forward that does not wait must not fail silently: the overflow surfaces at the frame's own backward ...
+        st.r_hint = 16
+        with pytest.raises(RuntimeError, match="rendered empty"):
+            helpers.run_ours(cam, g, cuda_device, grads=scene.upstream_grads(cam, seed=5))
+        assert st.r_hint >= o.num_rendered  # ... and the capacity has been raised: the next frame is complete again
+        ours = helpers.run_ours(cam, g, cuda_device, grads=scene.upstream_grads(cam, seed=5))
+        helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, label="after overflow")
+        # ... or, for a forward without a backward, at the next rasterizer call
+        st.r_hint = 16
+        helpers.run_ours(cam, g, cuda_device)
+        torch.cuda.synchronize()
+        with pytest.raises(RuntimeError, match="rendered empty"):
+            helpers.run_ours(cam, g, cuda_device)
+        ours = helpers.run_ours(cam, g, cuda_device)
+        helpers.compare_outputs(ours, oracle_outputs(o), tie=o.tie, label="after overflow 2")
+    finally:
+        rasterizer.set_capacity_checks("auto", cuda_device)
+        try:
+            st.reap(block=True)
+        except RuntimeError:
+            pass
 
 
 def test_two_forwards_then_two_backwards(cuda_device):
