@@ -174,6 +174,35 @@ int rtg_icp_fill_model_depth(float *render_depth, const float *frame_depth, cons
                              const float *frame_normal, int32_t H, int32_t W, float distance_threshold,
                              float normal_threshold, void *stream);
 
+/* Whole pyramid in one launch: build_vertex_pyramid + build_normal_pyramid (SLAM/utils.py:511-527) as IcpTracker.
+ * update_curr_status / predict_pose call them (SLAM/icp.py:385-395,423-425). Level l max-pools `depth` (H,W) by pools[l]
+ * and back-projects with the level intrinsics {fx,fy,cx,cy}[l] (K*downscale, SLAM/utils.py:517-519); vertex_out[l] /
+ * normal_out[l] are device (H/pools[l], W/pools[l], 3) buffers. 1 <= n_levels <= 4. One cooperative launch (max-pool +
+ * vertices of all levels, grid barrier for the per-level depth extremes, normals). */
+int rtg_icp_build_pyramid(const float *depth, int32_t H, int32_t W, int32_t n_levels, const int32_t *pools, const float *fx,
+                          const float *fy, const float *cx, const float *cy, float *const *vertex_out, float *const *normal_out,
+                          void *ws, void *stream);
+
+/* IcpTracker.predict_pose (SLAM/icp.py:417-452) in one cooperative launch: for every level (coarse to fine) `iters`
+ * Gauss-Newton iterations as in rtg_icp_solve_level, the pose carried from level to level starting at pose_init (device,
+ * 16 floats; NULL = identity), then point2plane_loss of the final pose on (p2p_vertex_t0, p2p_vertex_t1, p2p_normal_t0),
+ * each (p2p_H, p2p_W, 3). In every level "0" is the CURRENT frame and "1" the previous / model frame (the argument swap of
+ * SLAM/icp.py:438-441). out: 18 device floats = pose (row-major 4x4), loss, valid ratio of the last iteration; out_host
+ * (may be NULL): the same 18 floats written straight into mapped pinned host memory by the kernel, valid once work
+ * enqueued after this call on `stream` has been reached (record an event and wait for it) -- the only read-back of a
+ * predict_pose. */
+typedef struct RtgIcpLevel {
+    const float *vertex0, *normal0, *vertex1, *normal1; /* (H,W,3) channels-last, device */
+    int32_t H, W;
+    float fx, fy, cx, cy;
+    int32_t iters;
+    int32_t _pad;
+} RtgIcpLevel;
+int rtg_icp_predict_pose(const RtgIcpLevel *levels, int32_t n_levels, float distance_threshold, float normal_cos_threshold,
+                         float damping, const float *pose_init, const float *p2p_vertex_t0, const float *p2p_vertex_t1,
+                         const float *p2p_normal_t0, int32_t p2p_H, int32_t p2p_W, float *out, float *out_host, void *ws,
+                         void *stream);
+
 /* ---- image-space glue between the rasterizer forward and backward -------------
  * Fused masked L1 colour + depth loss of Mapping.loss_update (SLAM/multiprocess/mapper.py:402-431,444-451, with
  * l1_loss of utils/loss_utils.py:27-31) and its gradients w.r.t. the rendered colour and depth:
@@ -234,6 +263,30 @@ int rtg_transmission_tile_mask(int32_t H, int32_t W, const float *T_map, float r
 /* colour error image of mapper.py:481-487: sum over channels of |render - gt|, 0 where the rendered pixel is black;
  * render, gt (3,H,W), out (H,W). */
 int rtg_color_error(int32_t H, int32_t W, const float *render, const float *gt, float *out, void *stream);
+
+/* ---- map surgery on the Gaussian SoA and nearest neighbours ----------------------------
+ * rtg_soa_compact: GaussianPointCloud.delete / remove (SLAM/gaussian_pointcloud.py:195-235) -- keep the rows whose mask
+ * byte is non-zero (invert = 0) or zero (invert = 1; `delete(mask)` keeps ~mask) of n_arrays attribute arrays that share the
+ * row index; array a has words_per_row[a] 4-byte words per row (xyz 3, features_rest 45, rotation 4, counters 1, ...).
+ * One scan of the mask, one gather launch for all arrays; rows keep their order. out[a] must hold P rows; n_kept (device
+ * uint32) and n_kept_host (mapped pinned uint32, may be NULL) receive the number of rows kept. n_arrays <= 16.
+ * ws: rtg_soa_compact_workspace_bytes(P) bytes. in / out: host arrays of device pointers. */
+#define RTG_SOA_MAX_ARRAYS 16
+size_t rtg_soa_compact_workspace_bytes(int64_t P);
+int rtg_soa_compact(const uint8_t *mask, int32_t invert, int64_t P, int32_t n_arrays, const void *const *in, void *const *out,
+                    const int32_t *words_per_row, uint32_t *n_kept, uint32_t *n_kept_host, void *ws, void *stream);
+
+/* rtg_knn: exact K nearest reference points of every query point, 1 <= K <= 8, squared Euclidean distances ascending.
+ * Replaces distCUDA2 of submodules/simple-knn (simple_knn.cu:169-251; spatial.cu) as GaussianPointCloud.update_geometry
+ * uses it (gaussian_pointcloud.py:376: query == ref, K = 3, skip_self = 1, out_mean = (d0+d1+d2)/3 and out_idx) and
+ * pytorch3d.ops.knn_points as Mapping.temp_points_filter / gaussians_isolated call it (mapper.py:812-819,903-910:
+ * skip_self = 0). query (n_query,3), ref (n_ref,3) fp32; out_d2 (n_query,K), out_idx (n_query,K) int32, out_mean (n_query)
+ * -- each may be NULL. With fewer than K candidates the missing slots hold FLT_MAX / INT_MAX (simple-knn's sentinels).
+ * Uniform-grid search sized on the device from the bounding box of `ref`; no host synchronisation.
+ * ws: rtg_knn_workspace_bytes(n_ref) bytes. */
+size_t rtg_knn_workspace_bytes(int64_t n_ref);
+int rtg_knn(const float *query, int64_t n_query, const float *ref, int64_t n_ref, int32_t K, int32_t skip_self, float *out_d2,
+            int32_t *out_idx, float *out_mean, void *ws, void *stream);
 
 /* ---- measurement hook (no reference counterpart) ---------------------------------------------
  * When enabled, every kernel launch of this library is bracketed by CUDA events on its launching stream.

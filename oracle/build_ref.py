@@ -62,5 +62,29 @@ def build_cuda_utils():
     return 0
 
 
+def build_simple_knn():
+    """submodules/simple-knn (distCUDA2): same recipe; gcc 13 additionally needs <cfloat> / <climits> for
+    FLT_MAX / INT_MAX (simple_knn.cu:90,176-177). Module `_C` kept under oracle/_ref/simple_knn/."""
+    ref = "/root/reference/submodules/simple-knn"
+    out = os.path.join(OUT, "simple_knn")
+    if not os.path.isdir(ref):
+        return 0
+    if glob.glob(os.path.join(out, "_C*.so")) and "--force" not in sys.argv:
+        print("oracle/_ref/simple_knn already built")
+        return 0
+    os.makedirs(out, exist_ok=True)
+    tmp = "/tmp/rtg_refbuild_simple_knn"
+    shutil.rmtree(tmp, ignore_errors=True)
+    shutil.copytree(ref, tmp)
+    env = dict(os.environ, NVCC_APPEND_FLAGS="-include cstdint -include cfloat -include climits", TORCH_CUDA_ARCH_LIST="10.0",
+               MAX_JOBS="8")
+    subprocess.check_call([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=tmp, env=env)
+    so = glob.glob(os.path.join(tmp, "simple_knn", "_C*.so"))
+    assert so, "simple-knn build produced no extension"
+    shutil.copy(so[0], out)
+    print("built", os.path.join(out, os.path.basename(so[0])))
+    return 0
+
+
 if __name__ == "__main__":
-    sys.exit(main() or build_cuda_utils())
+    sys.exit(main() or build_cuda_utils() or build_simple_knn())

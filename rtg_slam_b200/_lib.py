@@ -34,6 +34,12 @@ class RtgAdamGroup(C.Structure):
     ]
 
 
+class RtgIcpLevel(C.Structure):
+    _fields_ = [("vertex0", C.c_void_p), ("normal0", C.c_void_p), ("vertex1", C.c_void_p), ("normal1", C.c_void_p),
+                ("H", C.c_int32), ("W", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("iters", C.c_int32), ("_pad", C.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/rtg_splat_b200.h
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _BWD_ARGS = [C.POINTER(RtgSplatView), _I32, _I32] + [_VP] * 6 + [_VP, _VP, _VP, _VP, _I64, _VP] + [_VP] * 4 + [_VP] + [_VP] * 8 + [_VP]
@@ -50,6 +56,8 @@ SIGNATURES = {
     "rtg_icp_workspace_bytes": (C.c_size_t, [_I32, _I32]),
     "rtg_icp_build_level": (C.c_int, [_VP, _I32, _I32, _I32, _F, _F, _F, _F, _VP, _VP, _VP, _VP]),
     "rtg_icp_solve_level": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _F, _F, _F, _F, _F, _I32, _VP, _VP, _VP, _VP]),
+    "rtg_icp_build_pyramid": (C.c_int, [_VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rtg_icp_predict_pose": (C.c_int, [_VP, _I32, _F, _F, _F, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "rtg_icp_point2plane_loss": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "rtg_icp_fill_model_depth": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _VP]),
     "rtg_loss_workspace_bytes": (C.c_size_t, []),
@@ -60,6 +68,10 @@ SIGNATURES = {
     "rtg_tile_mean": (C.c_int, [_I32, _I32, _VP, _F, _VP, _VP, _VP]),
     "rtg_transmission_tile_mask": (C.c_int, [_I32, _I32, _VP, _F, _VP, _VP, _VP]),
     "rtg_color_error": (C.c_int, [_I32, _I32, _VP, _VP, _VP, _VP]),
+    "rtg_soa_compact_workspace_bytes": (C.c_size_t, [_I64]),
+    "rtg_soa_compact": (C.c_int, [_VP, _I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rtg_knn_workspace_bytes": (C.c_size_t, [_I64]),
+    "rtg_knn": (C.c_int, [_VP, _I64, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP, _VP]),
     "rtg_profile_enable": (C.c_int, [_I32]),
     "rtg_profile_kernel_count": (C.c_int, []),
     "rtg_profile_kernel_name": (C.c_char_p, [_I32]),

@@ -10,6 +10,7 @@
 #include "prof.h"
 #include <vector>
 #include <mutex>
+#include <utility>
 
 namespace rtg {
 int launch_adam(const RtgAdamGroup *groups, int n_groups, float beta1, float beta2, float eps, int step, cudaStream_t s);
@@ -184,7 +185,7 @@ int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const floa
     rtg::ImgState img = rtg::img_from(img_ws, (size_t)vp.H * vp.W);
     rtg::BinState b = rtg::bin_from(bin_ws, (size_t)T, (size_t)R_cap);
 
-    // tile_count, tile_fill and tile_touched are adjacent (bin_from): one clear
+    // tile_count, tile_fill, tile_touched and vis_count are adjacent (bin_from): one clear
     cudaError_t e = cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)b.tile_offset - (char *)b.tile_count), s);
     if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward memset: ") + cudaGetErrorString(e));
     rtg::launch_preprocess_fwd(vp, P, M, means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp, tile_mask, g,
@@ -242,8 +243,7 @@ static int splat_backward_impl(int phase, const RtgSplatView *view, int32_t P, i
         rtg::launch_bwd_zero(P, M, shs != nullptr, cov3D_precomp == nullptr, radii, dL_dmeans3D, dL_dsh, dL_dcolors_precomp,
                              dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, forked ? ss->stream : s);
         if (forked) cudaEventRecord(ss->join, ss->stream);
-        rtg::launch_render_bwd(vp, g, b, img, counters, means3D, scales, rotations, final_T, hit_image, dL_dcolor, dL_ddepth,
-                               grad2d_scratch, s);
+        rtg::launch_render_bwd(vp, g, b, img, counters, final_T, hit_image, dL_dcolor, dL_ddepth, grad2d_scratch, s);
         if (forked) cudaStreamWaitEvent(s, ss->join, 0);  // enqueued after both: the zero-fill still overlaps render_bwd
     }
     if (phase != 1)
@@ -308,6 +308,59 @@ int rtg_icp_solve_level(const float *vertex0, const float *normal0, const float 
     rtg::launch_icp_solve_level(vertex0, normal0, vertex1, normal1, H, W, fx, fy, cx, cy, distance_threshold, normal_cos_threshold,
                                 damping, iters, pose, valid_ratio, ws, reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_icp_solve_level");
+}
+
+int rtg_icp_build_pyramid(const float *depth, int32_t H, int32_t W, int32_t n_levels, const int32_t *pools, const float *fx,
+                          const float *fy, const float *cx, const float *cy, float *const *vertex_out, float *const *normal_out,
+                          void *ws, void *stream) {
+    if (!depth || !pools || !fx || !fy || !cx || !cy || !vertex_out || !normal_out || !ws || H <= 0 || W <= 0 || n_levels < 1 ||
+        n_levels > RTG_ICP_MAX_LEVELS)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_build_pyramid: bad arguments");
+    rtg::IcpPyramid p;
+    p.depth = depth; p.H = H; p.W = W; p.n_levels = n_levels;
+    for (int l = 0; l < n_levels; l++) {
+        if (pools[l] < 1 || H / pools[l] < 1 || W / pools[l] < 1 || !vertex_out[l] || !normal_out[l])
+            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_build_pyramid: bad level");
+        p.pool[l] = pools[l]; p.fx[l] = fx[l]; p.fy[l] = fy[l]; p.cx[l] = cx[l]; p.cy[l] = cy[l];
+        p.vertex[l] = vertex_out[l]; p.normal[l] = normal_out[l];
+    }
+    // the grid is sized for the finest level: order the levels so that the last one has the smallest pool
+    int finest = 0;
+    for (int l = 1; l < n_levels; l++)
+        if (p.pool[l] < p.pool[finest]) finest = l;
+    if (finest != n_levels - 1) {
+        std::swap(p.pool[finest], p.pool[n_levels - 1]); std::swap(p.fx[finest], p.fx[n_levels - 1]);
+        std::swap(p.fy[finest], p.fy[n_levels - 1]); std::swap(p.cx[finest], p.cx[n_levels - 1]);
+        std::swap(p.cy[finest], p.cy[n_levels - 1]); std::swap(p.vertex[finest], p.vertex[n_levels - 1]);
+        std::swap(p.normal[finest], p.normal[n_levels - 1]);
+    }
+    cudaError_t e = rtg::launch_icp_pyramid(p, ws, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_icp_build_pyramid: ") + cudaGetErrorString(e));
+    return check_launch("rtg_icp_build_pyramid");
+}
+
+int rtg_icp_predict_pose(const RtgIcpLevel *levels, int32_t n_levels, float distance_threshold, float normal_cos_threshold,
+                         float damping, const float *pose_init, const float *p2p_vertex_t0, const float *p2p_vertex_t1,
+                         const float *p2p_normal_t0, int32_t p2p_H, int32_t p2p_W, float *out, float *out_host, void *ws,
+                         void *stream) {
+    if (!levels || n_levels < 1 || n_levels > RTG_ICP_MAX_LEVELS || !p2p_vertex_t0 || !p2p_vertex_t1 || !p2p_normal_t0 || p2p_H <= 0 ||
+        p2p_W <= 0 || !out || !ws)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_predict_pose: bad arguments");
+    rtg::IcpPredict p;
+    p.n_levels = n_levels;
+    for (int l = 0; l < n_levels; l++) {
+        const RtgIcpLevel &L = levels[l];
+        if (!L.vertex0 || !L.normal0 || !L.vertex1 || !L.normal1 || L.H <= 0 || L.W <= 0 || L.iters < 0)
+            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_icp_predict_pose: bad level");
+        p.lv[l] = rtg::IcpLevel{L.vertex0, L.normal0, L.vertex1, L.normal1, L.H, L.W, L.fx, L.fy, L.cx, L.cy, L.iters};
+    }
+    p.dist_thr = distance_threshold; p.cos_thr = normal_cos_threshold; p.damping = damping;
+    p.pose_in = pose_init;
+    p.p2p_v_t0 = p2p_vertex_t0; p.p2p_v_t1 = p2p_vertex_t1; p.p2p_n_t0 = p2p_normal_t0; p.p2p_HW = p2p_H * p2p_W;
+    p.out = out; p.out_host = out_host;
+    cudaError_t e = rtg::launch_icp_predict(p, ws, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_icp_predict_pose: ") + cudaGetErrorString(e));
+    return check_launch("rtg_icp_predict_pose");
 }
 
 int rtg_icp_point2plane_loss(const float *vertex_t0, const float *vertex_t1, const float *normal_t0, int32_t H, int32_t W,
@@ -396,6 +449,40 @@ int rtg_color_error(int32_t H, int32_t W, const float *render, const float *gt, 
     if (!render || !gt || !out || H <= 0 || W <= 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_color_error: bad arguments");
     rtg::launch_color_error(H, W, render, gt, out, reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_color_error");
+}
+
+size_t rtg_soa_compact_workspace_bytes(int64_t P) { return rtg::soa_compact_ws_bytes(P < 0 ? 0 : P); }
+
+int rtg_soa_compact(const uint8_t *mask, int32_t invert, int64_t P, int32_t n_arrays, const void *const *in, void *const *out,
+                    const int32_t *words_per_row, uint32_t *n_kept, uint32_t *n_kept_host, void *ws, void *stream) {
+    if (P < 0 || P > 0x7fffffffLL || n_arrays < 0 || n_arrays > RTG_SOA_MAX_ARRAYS || !n_kept)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_soa_compact: bad sizes");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (P == 0) {
+        cudaMemsetAsync(n_kept, 0, 4, s);
+        if (n_kept_host) *n_kept_host = 0;
+        return check_launch("rtg_soa_compact");
+    }
+    if (!mask || !ws || (n_arrays > 0 && (!in || !out || !words_per_row))) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_soa_compact: NULL pointer");
+    for (int i = 0; i < n_arrays; i++)
+        if (!in[i] || !out[i] || words_per_row[i] < 1 || in[i] == out[i])
+            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_soa_compact: bad array (NULL, in place, or words_per_row < 1)");
+    rtg::launch_soa_compact(mask, invert, P, n_arrays, in, out, words_per_row, n_kept, n_kept_host, ws, s);
+    return check_launch("rtg_soa_compact");
+}
+
+size_t rtg_knn_workspace_bytes(int64_t n_ref) { return rtg::knn_ws_bytes(n_ref < 0 ? 0 : n_ref); }
+
+int rtg_knn(const float *query, int64_t n_query, const float *ref, int64_t n_ref, int32_t K, int32_t skip_self, float *out_d2,
+            int32_t *out_idx, float *out_mean, void *ws, void *stream) {
+    if (n_query < 0 || n_ref < 0 || n_query > 0x7fffffffLL || n_ref > 0x7fffffffLL || K < 1 || K > 8)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_knn: bad sizes (1 <= K <= 8)");
+    if (n_query == 0) return RTG_OK;
+    if (!query || !ws || (n_ref > 0 && !ref)) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_knn: NULL pointer");
+    if (skip_self && (n_query != n_ref)) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_knn: skip_self needs query == ref");
+    if (rtg::launch_knn(query, n_query, ref, n_ref, K, skip_self, out_d2, out_idx, out_mean, ws, reinterpret_cast<cudaStream_t>(stream)))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_knn: unsupported K");
+    return check_launch("rtg_knn");
 }
 
 int rtg_profile_enable(int32_t on) {

@@ -15,7 +15,9 @@ namespace rtg {
 // Slots 3..8 hold the six moments  sum u, u dx, u dy, u dx^2, u dx dy, u dy^2  of u = (opacity * G) * dL/dalpha over the
 // blended (pixel, Gaussian) pairs (d = centre - pixel): every 2-D gradient of backward.cu:926-995 is a fixed linear
 // combination of them (moments_to_grad2d), formed once per Gaussian by the per-Gaussian backward pass.
-enum { REC_COLOR = 0, REC_M0 = 3, REC_MX = 4, REC_MY = 5, REC_MXX = 6, REC_MXY = 7, REC_MYY = 8, REC_DMEAN = 9, REC_DROT = 12 };
+// Slots 9..11: depth-path dL/dmean (world); 12..14: depth-path dL/d(surfel normal) (world; the quaternion chain is applied
+// by the per-Gaussian pass); 15: unused.
+enum { REC_COLOR = 0, REC_M0 = 3, REC_MX = 4, REC_MY = 5, REC_MXX = 6, REC_MXY = 7, REC_MYY = 8, REC_DMEAN = 9, REC_DNORMAL = 12 };
 
 struct ViewParams {
     int H, W, tiles_x, tiles_y;
@@ -60,9 +62,9 @@ static inline T *carve(char *&p, size_t n) {
     return r;
 }
 
-// Words per tile in the two atomic counter arrays (tile histogram, scatter cursor): counter of tile t is element
-// t * RTG_CNT_STRIDE. L2 atomics on the same 32-byte sector serialise, so neighbouring tiles do not share one
-// (measured: scatter 0.077 -> 0.060 ms; splitting a tile's counter further into sub-buckets gained nothing).
+// Words per tile in the tile histogram: counter of tile t is element t * RTG_CNT_STRIDE. L2 atomics on the same 32-byte
+// sector serialise, so neighbouring tiles do not share one (measured in round 1 on the then separate scatter cursors:
+// 0.077 -> 0.060 ms; splitting a tile's counter further into sub-buckets gained nothing).
 #ifndef RTG_CNT_STRIDE
 #define RTG_CNT_STRIDE 8
 #endif

@@ -27,8 +27,8 @@ void launch_render_fwd(const ViewParams &vp, const GeomState &g, const BinState 
                        float *out_color, float *out_depth, int *out_hit_color, int *out_hit_depth, float *out_hcw,
                        float *out_hdw, float *out_T, cudaStream_t s);
 void launch_render_bwd(const ViewParams &vp, const GeomState &g, const BinState &b, const ImgState &img, const int32_t *counters,
-                       const float *means, const float *scales, const float *rots, const float *final_T, const int *hit_image,
-                       const float *dL_dcolor, const float *dL_ddepth, float *rec, cudaStream_t s);
+                       const float *final_T, const int *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *rec,
+                       cudaStream_t s);
 
 // mapstats.cu
 void launch_gs_error(int H, int W, int P, const float *color_err, const float *depth_err, const float *normal_err,
@@ -44,5 +44,43 @@ void launch_frame_preprocess(const float *depth_in, int H, int W, int filter, in
                              float *depth_out, float *vertex, float *normal, float *confidence, uint8_t *invalid, void *ws,
                              cudaStream_t s);
 
-// adam.cu / icp.cu declared in their own sections of capi.cu
+// icp.cu: persistent (cooperative) kernels
+#define RTG_ICP_MAX_LEVELS 4
+struct IcpLevel {
+    const float *v0, *n0, *v1, *n1;  // "0" = current frame, "1" = previous / model frame
+    int H, W;
+    float fx, fy, cx, cy;
+    int iters;
+};
+struct IcpPredict {
+    IcpLevel lv[RTG_ICP_MAX_LEVELS];
+    int n_levels;
+    float dist_thr, cos_thr, damping;
+    const float *pose_in;
+    const float *p2p_v_t0, *p2p_v_t1, *p2p_n_t0;
+    int p2p_HW;
+    float *out, *out_host;
+};
+struct IcpPyramid {
+    const float *depth;
+    int H, W, n_levels;
+    int pool[RTG_ICP_MAX_LEVELS];
+    float fx[RTG_ICP_MAX_LEVELS], fy[RTG_ICP_MAX_LEVELS], cx[RTG_ICP_MAX_LEVELS], cy[RTG_ICP_MAX_LEVELS];
+    float *vertex[RTG_ICP_MAX_LEVELS], *normal[RTG_ICP_MAX_LEVELS];
+};
+cudaError_t launch_icp_predict(const IcpPredict &prm, void *ws, cudaStream_t s);
+cudaError_t launch_icp_pyramid(const IcpPyramid &prm, void *ws, cudaStream_t s);
+
+// mapsurgery.cu
+#ifndef RTG_SOA_MAX_ARRAYS
+#define RTG_SOA_MAX_ARRAYS 16
+#endif
+size_t soa_compact_ws_bytes(int64_t P);
+void launch_soa_compact(const uint8_t *mask, int invert, int64_t P, int n_arrays, const void *const *in, void *const *out,
+                        const int32_t *words_per_row, uint32_t *n_kept, uint32_t *n_kept_host, void *ws, cudaStream_t s);
+size_t knn_ws_bytes(int64_t n_ref);
+int launch_knn(const float *query, int64_t n_query, const float *ref, int64_t n_ref, int K, int skip_self, float *out_d2, int32_t *out_idx,
+               float *out_mean, void *ws, cudaStream_t s);
+
+// adam.cu and the per-level icp.cu entry points are declared in their own sections of capi.cu
 }  // namespace rtg

@@ -468,7 +468,8 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
     const float dcon[3] = {-0.5f * mxx, -0.5f * mxy, -0.5f * myy};  // conic.x, conic.y, conic.w
     const float dopac = m0 / sp0.w;
     float3 dmean = make_float3(rc.y, rc.z, rc.w);  // depth path
-    float4 drot = rd;                              // depth path
+    const float3 dnrm = make_float3(rd.x, rd.y, rd.z);  // depth path: dL/d(surfel normal), world space
+    float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const float3 mean = make_float3(means[i3], means[i3 + 1], means[i3 + 2]);
     if (has_sh) {
@@ -485,6 +486,27 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
         q = reinterpret_cast<const float4 *>(rots)[idx];
         quat_to_R(q, R);
         cov3d_from(sc, vp.scale_modifier, R, c6);
+        // depth path: the surfel normal is column argmin(scale) of R(q); d(normal)/dq of propagateRotationGrad
+        // (backward.cu:100-148) applied to the accumulated dL/dnormal
+        const int axis = arg_min3(sc.x, sc.y, sc.z);
+        const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+        const float w1 = dnrm.x, w2 = dnrm.y, w3 = dnrm.z;
+        if (axis == 0) {
+            drot.x = w2 * (2 * q3) + w3 * (-2 * q2);
+            drot.y = w2 * (2 * q2) + w3 * (2 * q3);
+            drot.z = w1 * (-4 * q2) + w2 * (2 * q1) + w3 * (-2 * q0);
+            drot.w = w1 * (-4 * q3) + w2 * (2 * q0) + w3 * (2 * q1);
+        } else if (axis == 1) {
+            drot.x = w1 * (-2 * q3) + w3 * (2 * q1);
+            drot.y = w1 * (2 * q2) + w2 * (-4 * q1) + w3 * (2 * q0);
+            drot.z = w1 * (2 * q1) + w3 * (2 * q3);
+            drot.w = w1 * (-2 * q0) + w2 * (-4 * q3) + w3 * (2 * q2);
+        } else {
+            drot.x = w1 * (2 * q2) + w2 * (-2 * q1);
+            drot.y = w1 * (2 * q3) + w2 * (-2 * q0) + w3 * (-4 * q1);
+            drot.z = w1 * (2 * q0) + w2 * (2 * q3) + w3 * (-4 * q2);
+            drot.w = w1 * (2 * q1) + w2 * (2 * q2);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 6; i++) c6[i] = cov3D_precomp[6 * (size_t)idx + i];

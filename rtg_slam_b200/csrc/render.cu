@@ -307,9 +307,11 @@ __device__ __forceinline__ int reduce9_slot(const int lane) {
 }
 
 // Depth-hit gradient of one pixel (backward.cu:997-1065): the first opaque Gaussian of the pixel receives the gradient
-// of the rendered depth w.r.t. its centre and, on the plane branch, w.r.t. its quaternion (through the surfel normal).
-__device__ __forceinline__ void depth_hit_grad(const ViewParams &vp, const GeomState &g, const float *__restrict__ scales,
-                                               const float *__restrict__ rots, const int *__restrict__ hit_image,
+// of the rendered depth w.r.t. its centre and, on the plane branch, w.r.t. its surfel normal. The normal is a column of
+// R(q): the chain to the quaternion (propagateRotationGrad, backward.cu:100-148) is linear in dL/dnormal, so the
+// world-space dL/dnormal is what accumulates in the record and the per-Gaussian pass, which owns the quaternion, applies
+// the chain once per Gaussian. This kernel therefore reads no parameter array, only the forward's records.
+__device__ __forceinline__ void depth_hit_grad(const ViewParams &vp, const GeomState &g, const int *__restrict__ hit_image,
                                                const float *__restrict__ dL_ddepth, float *__restrict__ rec, const int px,
                                                const int py, const int pix_id, const bool inside) {
     if (inside) {
@@ -319,9 +321,9 @@ __device__ __forceinline__ void depth_hit_grad(const ViewParams &vp, const GeomS
             const float4 h0 = __ldg(g.hit + 2 * (size_t)gid), h1 = __ldg(g.hit + 2 * (size_t)gid + 1);
             const float3 nc = make_float3(h0.x, h0.y, h0.z);
             const float3 pc = make_float3(h1.x, h1.y, h1.z);
-            float3 sc = make_float3(0.f, 0.f, 0.f);
-            if (scales != nullptr) sc = make_float3(scales[3 * (size_t)gid], scales[3 * (size_t)gid + 1], scales[3 * (size_t)gid + 2]);
-            const float scale_max = fmaxf(fmaxf(sc.x, sc.y), sc.z);  // no scale_modifier here (backward.cu:1009)
+            // max(scales) without the scale modifier (backward.cu:1009); the record holds scale_max * scale_modifier
+            // (exact for scale_modifier == 1, the only value the reference's callers pass, SLAM/render.py:41)
+            const float scale_max = h0.w / vp.scale_modifier;
             const float num = pc.x * nc.x + pc.y * nc.y + pc.z * nc.z;
             const float ndotr = nc.x * ray.x + nc.y * ray.y + nc.z * ray.z;
             const float t = (float)((double)num / ((double)ndotr + 1e-8));
@@ -341,36 +343,13 @@ __device__ __forceinline__ void depth_hit_grad(const ViewParams &vp, const GeomS
                 atomicAdd(r + REC_DMEAN + 0, dL_ddi * (dpx * v0 + dpy * v1 + dpz * v2));
                 atomicAdd(r + REC_DMEAN + 1, dL_ddi * (dpx * v4 + dpy * v5 + dpz * v6));
                 atomicAdd(r + REC_DMEAN + 2, dL_ddi * (dpx * v8 + dpy * v9 + dpz * v10));
-                const int axis = arg_min3(sc.x, sc.y, sc.z);
                 const float n1 = ray.z * (nr * pc.x - np_ * ray.x) * inv_nr2;
                 const float n2 = ray.z * (nr * pc.y - np_ * ray.y) * inv_nr2;
                 const float n3 = ray.z * (nr * pc.z - np_ * ray.z) * inv_nr2;
-                const float w1 = n1 * v0 + n2 * v1 + n3 * v2;
-                const float w2 = n1 * v4 + n2 * v5 + n3 * v6;
-                const float w3 = n1 * v8 + n2 * v9 + n3 * v10;
-                const float4 q = reinterpret_cast<const float4 *>(rots)[gid];
-                const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
-                float d0[3], d1[3], d2[3], d3[3];  // d(normal)/dq_k (propagateRotationGrad, backward.cu:100-148)
-                if (axis == 0) {
-                    d0[0] = 0; d0[1] = 2 * q3; d0[2] = -2 * q2;
-                    d1[0] = 0; d1[1] = 2 * q2; d1[2] = 2 * q3;
-                    d2[0] = -4 * q2; d2[1] = 2 * q1; d2[2] = -2 * q0;
-                    d3[0] = -4 * q3; d3[1] = 2 * q0; d3[2] = 2 * q1;
-                } else if (axis == 1) {
-                    d0[0] = -2 * q3; d0[1] = 0; d0[2] = 2 * q1;
-                    d1[0] = 2 * q2; d1[1] = -4 * q1; d1[2] = 2 * q0;
-                    d2[0] = 2 * q1; d2[1] = 0; d2[2] = 2 * q3;
-                    d3[0] = -2 * q0; d3[1] = -4 * q3; d3[2] = 2 * q2;
-                } else {
-                    d0[0] = 2 * q2; d0[1] = -2 * q1; d0[2] = 0;
-                    d1[0] = 2 * q3; d1[1] = -2 * q0; d1[2] = -4 * q1;
-                    d2[0] = 2 * q0; d2[1] = 2 * q3; d2[2] = -4 * q2;
-                    d3[0] = 2 * q1; d3[1] = 2 * q2; d3[2] = 0;
-                }
-                atomicAdd(r + REC_DROT + 0, dL_ddi * (w1 * d0[0] + w2 * d0[1] + w3 * d0[2]));
-                atomicAdd(r + REC_DROT + 1, dL_ddi * (w1 * d1[0] + w2 * d1[1] + w3 * d1[2]));
-                atomicAdd(r + REC_DROT + 2, dL_ddi * (w1 * d2[0] + w2 * d2[1] + w3 * d2[2]));
-                atomicAdd(r + REC_DROT + 3, dL_ddi * (w1 * d3[0] + w2 * d3[1] + w3 * d3[2]));
+                // view-space dL/dnormal -> world space
+                atomicAdd(r + REC_DNORMAL + 0, dL_ddi * (n1 * v0 + n2 * v1 + n3 * v2));
+                atomicAdd(r + REC_DNORMAL + 1, dL_ddi * (n1 * v4 + n2 * v5 + n3 * v6));
+                atomicAdd(r + REC_DNORMAL + 2, dL_ddi * (n1 * v8 + n2 * v9 + n3 * v10));
             } else {
                 atomicAdd(r + REC_DMEAN + 0, dL_ddi * __ldg(vm + 2));
                 atomicAdd(r + REC_DMEAN + 1, dL_ddi * __ldg(vm + 6));
@@ -423,10 +402,14 @@ __device__ __forceinline__ void bwd_blend(BwdPix &p, const float alpha, const fl
 #ifndef BWD_MIN_BLOCKS
 #define BWD_MIN_BLOCKS 6
 #endif
-__global__ void __launch_bounds__(BWD_THREADS, BWD_MIN_BLOCKS) render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b,
+#if BWD_MIN_BLOCKS > 0
+#define BWD_BOUNDS __launch_bounds__(BWD_THREADS, BWD_MIN_BLOCKS)
+#else
+#define BWD_BOUNDS __launch_bounds__(BWD_THREADS)
+#endif
+__global__ void BWD_BOUNDS render_bwd_kernel(const ViewParams vp, const GeomState g, const BinState b,
                                                                const ImgState img, const int *__restrict__ counters,
-                                                               const float *__restrict__ means, const float *__restrict__ scales,
-                                                               const float *__restrict__ rots, const float *__restrict__ final_T,
+                                                               const float *__restrict__ final_T,
                                                                const int *__restrict__ hit_image, const float *__restrict__ dL_dcolor,
                                                                const float *__restrict__ dL_ddepth, float *__restrict__ rec) {
     __shared__ float4 s_s0[BATCH];
@@ -571,8 +554,8 @@ __global__ void __launch_bounds__(BWD_THREADS, BWD_MIN_BLOCKS) render_bwd_kernel
         }
     }
 
-    depth_hit_grad(vp, g, scales, rots, hit_image, dL_ddepth, rec, px, pyA, pidA, insA);
-    depth_hit_grad(vp, g, scales, rots, hit_image, dL_ddepth, rec, px, pyB, pidB, insB);
+    depth_hit_grad(vp, g, hit_image, dL_ddepth, rec, px, pyA, pidA, insA);
+    depth_hit_grad(vp, g, hit_image, dL_ddepth, rec, px, pyB, pidB, insB);
 }
 
 void launch_render_fwd(const ViewParams &vp, const GeomState &g, const BinState &b, const ImgState &img, const int32_t *counters,
@@ -585,11 +568,11 @@ void launch_render_fwd(const ViewParams &vp, const GeomState &g, const BinState 
 }
 
 void launch_render_bwd(const ViewParams &vp, const GeomState &g, const BinState &b, const ImgState &img, const int32_t *counters,
-                       const float *means, const float *scales, const float *rots, const float *final_T, const int *hit_image,
-                       const float *dL_dcolor, const float *dL_ddepth, float *rec, cudaStream_t s) {
+                       const float *final_T, const int *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *rec,
+                       cudaStream_t s) {
     const int T = vp.tiles_x * vp.tiles_y;
     ProfScope ps(K_RENDER_BWD, s);
-    render_bwd_kernel<<<T, BWD_THREADS, 0, s>>>(vp, g, b, img, counters, means, scales, rots, final_T, hit_image, dL_dcolor, dL_ddepth, rec);
+    render_bwd_kernel<<<T, BWD_THREADS, 0, s>>>(vp, g, b, img, counters, final_T, hit_image, dL_dcolor, dL_ddepth, rec);
 }
 
 }  // namespace rtg

@@ -1,10 +1,11 @@
 """Frame-to-model projective point-to-plane ICP, API of the reference's SLAM/icp.py.
 
 `ICP` and `IcpTracker` keep the constructor arguments, method names, argument order and return values of
-the reference (SLAM/icp.py:16-48,357-452); the arithmetic runs in librtg_splat_b200.so: one kernel per
-pyramid level build, one kernel per Gauss-Newton iteration (residuals + Jacobians + 27-term reduction +
-damped 6x6 solve + exp_se3 + pose update on the device). A whole `predict_pose` issues ~25 launches and
-one 72-byte read-back, against ~600 eager ops and >= 45 host synchronisations in the reference."""
+the reference (SLAM/icp.py:16-48,357-452); the arithmetic runs in librtg_splat_b200.so. `IcpTracker.predict_pose`
+is ONE cooperative kernel (all levels x all Gauss-Newton iterations: residuals + Jacobians + 27-term reduction +
+damped 6x6 solve + exp_se3 + pose update, one grid barrier per iteration, then the point-to-plane loss) that writes
+its 72-byte result straight into pinned host memory, and a pyramid is one launch, against ~600 eager ops and >= 45
+host synchronisations in the reference. `ICP.icp` (one level) keeps the kernel-per-iteration entry point."""
 from __future__ import annotations
 
 import ctypes as C
@@ -25,6 +26,17 @@ def _p(t):
 
 
 _WS = {}
+_RES = {}
+
+
+def _result_buffers(device):
+    """(device 18 floats, mapped pinned 18 floats, event) of predict_pose, one set per device."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _RES:
+        _RES[idx] = (torch.zeros(18, dtype=torch.float32, device=torch.device("cuda", idx)),
+                     torch.zeros(18, dtype=torch.float32).pin_memory(), torch.cuda.Event())
+    return _RES[idx]
+
 
 
 def _workspace(device):
@@ -71,16 +83,25 @@ def build_level(depth, pool, fx, fy, cx, cy):
 
 
 def build_pyramids(depth, K, n_levels):
-    """build_vertex_pyramid + build_normal_pyramid (SLAM/utils.py:511-527): index 0 is the coarsest level."""
+    """build_vertex_pyramid + build_normal_pyramid (SLAM/utils.py:511-527): index 0 is the coarsest level.
+    One cooperative launch for all levels (rtg_icp_build_pyramid)."""
     fx, fy, cx, cy = K if isinstance(K, tuple) else _intrinsics(K)
-    vs, ns = [], []
-    for i in range(n_levels):
-        pool = 1 << (n_levels - 1 - i)
-        s = 1.0 / pool
-        v, n = build_level(depth, pool, np.float32(fx) * np.float32(s), np.float32(fy) * np.float32(s),
-                           np.float32(cx) * np.float32(s), np.float32(cy) * np.float32(s))
-        vs.append(v)
-        ns.append(n)
+    if not depth.is_cuda or depth.dtype != torch.float32:
+        raise TypeError("depth must be a CUDA float32 tensor")
+    if n_levels > 4:
+        raise ValueError("at most 4 pyramid levels")
+    L = _lib.lib()
+    d = depth.contiguous()
+    H, W = d.shape[:2]
+    pools = [1 << (n_levels - 1 - i) for i in range(n_levels)]
+    sc = [np.float32(1.0 / p) for p in pools]
+    vs = [torch.empty((H // p, W // p, 3), dtype=torch.float32, device=d.device) for p in pools]
+    ns = [torch.empty_like(v) for v in vs]
+    I32, F32, VP = C.c_int32 * n_levels, C.c_float * n_levels, C.c_void_p * n_levels
+    check(L.rtg_icp_build_pyramid(
+        _p(d), H, W, n_levels, I32(*pools), F32(*[np.float32(fx) * s for s in sc]), F32(*[np.float32(fy) * s for s in sc]),
+        F32(*[np.float32(cx) * s for s in sc]), F32(*[np.float32(cy) * s for s in sc]), VP(*[v.data_ptr() for v in vs]),
+        VP(*[n.data_ptr() for n in ns]), _p(_workspace(d.device)), _stream(d.device)), "rtg_icp_build_pyramid")
     return vs, ns
 
 
@@ -162,32 +183,41 @@ class IcpTracker:
         K = frame["K"]
         frame_id = frame["frame_id"]
         if self.vertex_pyramid_t0 is None:
-            # the reference evaluates point2plane_loss on a None pyramid here and raises; callers only reach
-            # this after move_last_status(), so keep the identity answer and report success
+            # the reference sets the identity pose and then subscripts the None pyramid in point2plane_loss
+            # (SLAM/icp.py:421-449): same exception type; callers only get here after move_last_status()
             self._set_K(K)
-            return np.eye(4), True
+            raise TypeError("'NoneType' object is not subscriptable (predict_pose before move_last_status: no previous frame)")
         L = _lib.lib()
         levels = len(self.icp_downscales)
         if self.icp_use_model_depth and frame_id >= self.icp_warmup_frames:
             self.vertex_pyramid_t0, self.normal_pyramid_t0 = build_pyramids(self.last_model_depth, self._Kf, levels)
         device = self.vertex_pyramid_t1[0].device
         Kf = _intrinsics(K) if K is not self.K else self._Kf
-        pose = torch.eye(4, dtype=torch.float32, device=device)
-        valid_ratio = torch.zeros((), dtype=torch.float32, device=device)
+        lv = (_lib.RtgIcpLevel * levels)()
+        keep = []
         for level in range(levels):
             s = np.float32(self.icp_downscales[level])
-            Kl = tuple(float(np.float32(k) * s) for k in Kf)
             # argument swap of the reference: "0" inside icp() is the CURRENT frame (SLAM/icp.py:438-441)
-            pose, valid_ratio = self.icp_trackers[level].icp(pose, self.vertex_pyramid_t1[level], self.vertex_pyramid_t0[level],
-                                                             self.normal_pyramid_t1[level], self.normal_pyramid_t0[level], Kl)
-        out = torch.empty(18, dtype=torch.float32, device=device)
-        out[:16] = pose.reshape(-1)
-        out[17] = valid_ratio
-        v_t0, v_t1, n_t0 = self.vertex_pyramid_t0[-1], self.vertex_pyramid_t1[-1], self.normal_pyramid_t0[-1]
+            v0, n0 = _map3(self.vertex_pyramid_t1[level], "vertex_t1"), _map3(self.normal_pyramid_t1[level], "normal_t1")
+            v1, n1 = _map3(self.vertex_pyramid_t0[level], "vertex_t0"), _map3(self.normal_pyramid_t0[level], "normal_t0")
+            keep += [v0, n0, v1, n1]
+            trk = self.icp_trackers[level]
+            e = lv[level]
+            e.vertex0, e.normal0, e.vertex1, e.normal1 = v0.data_ptr(), n0.data_ptr(), v1.data_ptr(), n1.data_ptr()
+            e.H, e.W = v0.shape[0], v0.shape[1]
+            e.fx, e.fy, e.cx, e.cy = (float(np.float32(k) * s) for k in Kf)
+            e.iters = int(trk.max_iterations)
+        t0 = self.icp_trackers[0]  # thresholds are shared by all levels (IcpTracker.__init__)
+        out, pinned, event = _result_buffers(device)
+        v_t0, v_t1, n_t0 = keep[-2], keep[-4], keep[-1]
         H, W = v_t0.shape[:2]
-        check(L.rtg_icp_point2plane_loss(_p(v_t0.contiguous()), _p(v_t1.contiguous()), _p(n_t0.contiguous()), H, W, _p(pose),
-                                         _p(out[16:17]), _p(_workspace(device)), _stream(device)), "rtg_icp_point2plane_loss")
-        host = out.cpu().numpy()  # the only read-back of the solve
+        stream = torch.cuda.current_stream(device)
+        check(L.rtg_icp_predict_pose(lv, levels, float(t0.distance_threshold), float(t0.normal_threshold), float(t0.damping), None,
+                                     _p(v_t0), _p(v_t1), _p(n_t0), H, W, _p(out), C.c_void_p(pinned.data_ptr()),
+                                     _p(_workspace(device)), C.c_void_p(stream.cuda_stream)), "rtg_icp_predict_pose")
+        event.record(stream)
+        event.synchronize()  # the only wait of the solve; the kernel wrote the 18 floats into pinned host memory itself
+        host = pinned.numpy().copy()
         pose_t1_t0 = host[:16].reshape(4, 4).astype(np.float32)
         self.last_p2ploss, self.last_valid_ratio = float(host[16]), float(host[17])
         if self.verbose:

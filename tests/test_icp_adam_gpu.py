@@ -170,3 +170,56 @@ def test_fused_loss_matches_the_reference_expressions(cuda_device, use_mask):
     assert int(parts[3]) == int(valid.sum())
     assert float((g1 - render.grad).abs().max()) < 1e-9 + 1e-5 * float(render.grad.abs().max())
     assert float((g2 - depth.grad).abs().max()) < 1e-9 + 1e-5 * float(depth.grad.abs().max())
+
+
+# ---------------------------------------------------------------- sequence-level tracking (BASELINE configs[3])
+@pytest.mark.parametrize("name", ["icp_sequence_ragged", "icp_sequence_tum"])
+def test_tracker_sequence_matches_reference_trajectory(cuda_device, name):
+    """IcpTracker driven over a synthetic TUM-like sequence the way SLAM/multiprocess/tracker.py:265-290 drives it, with
+    icp_use_model_depth=True (the setting of every shipped dataset config: the frame-to-MODEL association), against the
+    trajectory of the UNMODIFIED reference tracker on the same frames (tests/golden/make_icp_sequence_golden.py).
+    Tolerances of SURVEY 8(c): per-frame ||dT||_F < 1e-4, ATE within 1 mm of the reference trajectory."""
+    from golden.make_icp_sequence_golden import SEQUENCES, sequence_inputs, tracker_args as seq_args
+    from rtg_slam_b200 import icp as ricp
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = SEQUENCES[name]
+    cam = scene.make_camera(cfg["cam"])
+    Kt = torch.from_numpy(cam.K)
+    Kf = (cam.fx, cam.fy, cam.cx, cam.cy)
+    trk = ricp.IcpTracker(seq_args(cfg["use_model_depth"], cfg["warmup"]))
+    traj = [np.eye(4)]
+    for k in range(cfg["frames"]):
+        depth, model = sequence_inputs(name, k)
+        td = torch.from_numpy(depth).to(cuda_device)
+        trk.update_curr_status(td, Kt)
+        if k > 0:
+            pose, ok = trk.predict_pose({"K": Kt, "frame_id": k})
+            assert bool(ok) == bool(gold["success"][k - 1]), k
+            err = np.linalg.norm(pose.astype(np.float64) - gold["rel_poses"][k - 1].astype(np.float64))
+            assert err < 1e-4, f"frame {k}: ||dT||_F = {err:.2e}"
+            traj.append(traj[-1] @ pose.astype(np.float64))  # tracker.py:282
+        trk.move_last_status()
+        # the mapper's render of this frame becomes the next reference depth (slam.py -> tracker.update_last_status)
+        tm = torch.from_numpy(model).to(cuda_device)
+        _, rn = ricp.build_pyramids(tm, Kf, 1)
+        render_depth = tm[..., None].contiguous().clone()
+        trk.update_last_status(None, render_depth, td[..., None], rn[0], trk.normal_pyramid_t1[-1])
+        assert trk.last_model_depth is render_depth
+    traj = np.stack(traj)
+    d = traj[:, :3, 3] - gold["trajectory"][:, :3, 3]
+    ate_vs_ref = float(np.sqrt((d * d).sum(-1).mean()))
+    assert ate_vs_ref < 1e-3, ate_vs_ref
+    d = traj[:, :3, 3] - gold["gt"][:, :3, 3]
+    assert abs(float(np.sqrt((d * d).sum(-1).mean())) - float(gold["ate_vs_gt"])) < 1e-3
+
+
+def test_predict_pose_before_any_frame_raises_like_the_reference(cuda_device):
+    """SLAM/icp.py:421-449: with no previous frame the reference sets the identity pose and then evaluates
+    point2plane_loss on a None pyramid, i.e. raises TypeError; callers only get here after move_last_status()."""
+    from rtg_slam_b200 import icp as ricp
+    cam = scene.make_camera("small")
+    trk = ricp.IcpTracker(tracker_args())
+    Kt = torch.from_numpy(cam.K)
+    trk.update_curr_status(torch.from_numpy(scene.raycast_room_depth(cam)).to(cuda_device), Kt)
+    with pytest.raises(TypeError):
+        trk.predict_pose({"K": Kt, "frame_id": 0})
