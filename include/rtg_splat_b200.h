@@ -104,7 +104,8 @@ int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const flo
  * compositing backward and the per-Gaussian backward (tile-sharded multi-GPU rendering):
  *   rtg_splat_backward_render : zero-fill of the culled rows + backward of renderCUDA (backward.cu:808-1066); on return
  *                               `grad2d_scratch` holds, per Gaussian, the 16-float record of partial sums
- *                               {colour 3, mean2D 2, conic 3, opacity 1, depth-path mean 3, depth-path quaternion 4}
+ *                               {colour 3, six moments of opacity*G*dL/dalpha (the 2-D gradients are linear in them),
+ *                               depth-path dL/dmean 3, depth-path dL/d(surfel normal) 3, unused 1}
  *                               over the tiles this forward rendered -- sum it across ranks (e.g. ncclAllReduce);
  *   rtg_splat_backward_finish : computeCov2DCUDA + preprocessCUDA backward (backward.cu:273-548) from the records,
  *                               which it clears again. Visibility (radii) does not depend on tile_mask, so ranks
@@ -124,6 +125,49 @@ int rtg_splat_backward_finish(const RtgSplatView *view, int32_t P, int32_t M, co
                               const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch,
                               float *dL_dmeans3D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity,
                               float *dL_dscales, float *dL_drotations, float *dL_dcov3D, float *dL_dmeans2D, void *stream);
+
+/* ---- Gaussian-sharded rendering (BASELINE configs[4]) ----------------------------------
+ * Rank r owns the Gaussians [p_begin, p_end) of the P-Gaussian map (parameters, gradients, optimizer state: arrays of
+ * p_end - p_begin rows) and a subset of the 16x16 tiles. The forward of rtg_splat_forward is split around the exchange
+ * of the per-Gaussian records, the backward around the exchange of the gradient records:
+ *   rtg_splat_forward_preprocess  clears the binning counters and runs preprocessCUDA (forward.cu:238-354) on the owned
+ *                                 Gaussians: writes rows [p_begin, p_end) of the geometry workspace (sized for P) and of
+ *                                 `radii` (P entries) -- then all-gather those rows across ranks (their byte offsets inside
+ *                                 the workspace: rtg_splat_geom_layout; splat 32 B, colour 16 B, surfel 32 B per Gaussian);
+ *   rtg_splat_forward_render      tile histogram of ALL P records over the tiles of `tile_mask` (this rank's tiles), scan,
+ *                                 scatter, per-tile sort, compositing: outputs as rtg_splat_forward, valid on those tiles;
+ *   rtg_splat_backward_render_shard   compositing backward over this rank's tiles into `grad2d_scratch` (P records, zero on
+ *                                 entry) + zero-fill of the owned gradient rows -- then reduce-scatter the records so that
+ *                                 the owner of [p_begin, p_end) holds their sums;
+ *   rtg_splat_backward_finish_shard   per-Gaussian backward of the owned Gaussians; here `grad2d_scratch` must be indexable
+ *                                 at records [p_begin, p_end) (pass the reduce-scatter output minus p_begin records).
+ * In the *_shard calls means3D / shs / ... / dL_d* point to the OWNED rows (row 0 = Gaussian p_begin); radii, the
+ * workspaces and the image-sized arrays are global. */
+int rtg_splat_geom_layout(int32_t P, size_t *splat_offset, size_t *rgb_offset, size_t *hit_offset, size_t *vis_list_offset);
+int rtg_splat_forward_preprocess(const RtgSplatView *view, int32_t P, int32_t p_begin, int32_t p_end, int32_t M, const float *means3D,
+                                 const float *shs, const float *colors_precomp, const float *opacities, const float *scales,
+                                 const float *rotations, const float *cov3D_precomp, void *geom_ws, void *bin_ws, int64_t R_cap,
+                                 int32_t *radii, void *stream);
+int rtg_splat_forward_render(const RtgSplatView *view, int32_t P, const int32_t *tile_mask, void *geom_ws, void *img_ws, void *bin_ws,
+                             int64_t R_cap, float *out_color, float *out_depth, int32_t *out_hit_color, int32_t *out_hit_depth,
+                             float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, const int32_t *radii,
+                             int32_t *counters, int32_t *counters_host, void *scan_done_event, void *stream);
+int rtg_splat_backward_render_shard(int32_t p_begin, int32_t p_end, const RtgSplatView *view, int32_t P, int32_t M,
+                                    const float *means3D, const float *shs, const float *colors_precomp, const float *scales,
+                                    const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom_ws,
+                                    const void *img_ws, const void *bin_ws, int64_t R_cap, const int32_t *counters,
+                                    const float *final_T, const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth,
+                                    float *grad2d_scratch, float *dL_dmeans3D, float *dL_dsh, float *dL_dcolors_precomp,
+                                    float *dL_dopacity, float *dL_dscales, float *dL_drotations, float *dL_dcov3D,
+                                    float *dL_dmeans2D, void *stream);
+int rtg_splat_backward_finish_shard(int32_t p_begin, int32_t p_end, const RtgSplatView *view, int32_t P, int32_t M,
+                                    const float *means3D, const float *shs, const float *colors_precomp, const float *scales,
+                                    const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom_ws,
+                                    const void *img_ws, const void *bin_ws, int64_t R_cap, const int32_t *counters,
+                                    const float *final_T, const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth,
+                                    float *grad2d_scratch, float *dL_dmeans3D, float *dL_dsh, float *dL_dcolors_precomp,
+                                    float *dL_dopacity, float *dL_dscales, float *dL_drotations, float *dL_dcov3D,
+                                    float *dL_dmeans2D, void *stream);
 
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:21-26, rasterizer_impl.cu:145-157). */
 int rtg_splat_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

@@ -140,6 +140,60 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
     }
 }
 
+// ---------------------------------------------------------------- tile histogram from the records (Gaussian-sharded forward)
+// The single-GPU forward builds the histogram inside the forward preprocess. When the Gaussians are sharded over ranks,
+// every rank needs the histogram of ALL visible Gaussians over ITS tiles, which exists only after the records have been
+// exchanged: this pass recomputes it from the records with the same pair expansion and the bit-identical cut-off test.
+__global__ void __launch_bounds__(256) tile_histogram_kernel(const ViewParams vp, int P, const GeomState g, const int *__restrict__ radii,
+                                                             const int *__restrict__ tile_mask, BinState b) {
+    __shared__ uint32_t s_excl[8][32], s_rect[8][32];
+    __shared__ float4 s_ga[8][32], s_gb[8][32];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = idx < P ? radii[idx] : 0;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (r > 0) {
+        s0 = g.splat[2 * (size_t)idx];
+        s1 = g.splat[2 * (size_t)idx + 1];
+        tile_rect(make_float2(s0.x, s0.y), r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
+    }
+    const int npairs = (x1 - x0) * (y1 - y0);
+    const int incl = warp_incl_scan(npairs, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // warp-uniform
+    s_excl[w][lane] = (uint32_t)(incl - npairs);
+    s_rect[w][lane] = pack_rect(x0, y0, max(x1 - x0, 1));
+    const float2 nb = cut_slopes(s1.x, s1.y, s1.z);
+    s_ga[w][lane] = make_float4(s0.x, s0.y, s0.z, nb.x);
+    s_gb[w][lane] = make_float4(s1.x, s1.y, s1.z, nb.y);
+    __syncwarp();
+    for (int k = lane; k < total; k += 32) {
+        const int o = pair_owner(s_excl[w], (uint32_t)k);
+        const uint32_t local = (uint32_t)k - s_excl[w][o], rc = s_rect[w][o];
+        const uint32_t rw = rc >> 20;
+        int cx, cy;
+        rect_cell(local, rw, cx, cy);
+        const int x = (int)(rc & 1023u) + cx, y = (int)((rc >> 10) & 1023u) + cy;
+        const int t = y * vp.tiles_x + x;
+        if (__ldg(tile_mask + t)) {
+            const float4 ga = s_ga[w][o], gb = s_gb[w][o];
+            const float fx0 = (float)(x * RTG_TILE), fy0 = (float)(y * RTG_TILE);
+            if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, ga.w, gb.w, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1)))
+                b.tile_touched[t] = 1u;
+            else
+                atomicAdd(b.tile_count + (size_t)t * RTG_CNT_STRIDE, 1u);
+        }
+    }
+}
+
+void launch_tile_histogram(const ViewParams &vp, int P, const GeomState &g, const int *radii, const int *tile_mask, const BinState &b,
+                           cudaStream_t s) {
+    if (P <= 0) return;
+    ProfScope ps(K_PREPROCESS_FWD, s);
+    tile_histogram_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, g, radii, tile_mask, b);
+}
+
 // ---------------------------------------------------------------- per-tile depth sort
 #define SORT_THREADS 256
 #define SORT_SMEM_KEYS 4096

@@ -124,6 +124,17 @@ static rtg::ViewParams make_view(const RtgSplatView *v) {
     return p;
 }
 
+// rows of a LOCAL parameter array addressed with the global Gaussian id: base - p_begin rows (integer arithmetic: the
+// shifted value is only ever dereferenced at ids >= p_begin)
+template <typename T>
+static const T *shift_rows(const T *base, int64_t p_begin, size_t elems_per_row) {
+    return base ? reinterpret_cast<const T *>(reinterpret_cast<uintptr_t>(base) - (uintptr_t)p_begin * elems_per_row * sizeof(T)) : nullptr;
+}
+template <typename T>
+static T *shift_rows(T *base, int64_t p_begin, size_t elems_per_row) {
+    return base ? reinterpret_cast<T *>(reinterpret_cast<uintptr_t>(base) - (uintptr_t)p_begin * elems_per_row * sizeof(T)) : nullptr;
+}
+
 extern "C" {
 
 const char *rtg_last_error(void) { return g_err.c_str(); }
@@ -152,6 +163,57 @@ static int validate_view(const RtgSplatView *v, const char *who) {
     return RTG_OK;
 }
 
+static int validate_inputs(const char *who, const RtgSplatView *view, int32_t n, int32_t M, const float *means3D, const float *shs,
+                           const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
+                           const float *cov3D_precomp, const int32_t *radii) {
+    if (n <= 0) return RTG_OK;
+    if (!means3D || !opacities || !radii) return fail(RTG_ERR_INVALID_ARGUMENT, std::string(who) + ": NULL means3D / opacities / radii");
+    // same exactly-one-of rules as GaussianRasterizer.forward (__init__.py:335-347)
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "Please provide excatly one of either SHs or precomputed colors!");
+    if (((scales == nullptr || rotations == nullptr) && cov3D_precomp == nullptr) ||
+        ((scales != nullptr || rotations != nullptr) && cov3D_precomp != nullptr))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    if (shs && (M < (view->sh_degree + 1) * (view->sh_degree + 1) || M > 16))
+        return fail(RTG_ERR_INVALID_ARGUMENT, std::string(who) + ": M must hold (sh_degree+1)^2 coefficients and be <= 16");
+    if ((((uintptr_t)rotations) & 15) || (M == 16 && (((uintptr_t)shs) & 15)))
+        return fail(RTG_ERR_INVALID_ARGUMENT, std::string(who) + ": rotations / shs must be 16-byte aligned");
+    return RTG_OK;
+}
+
+// clear of the binning counters + forward preprocess of the Gaussians [p_begin, p_end); `fused_histogram`: the tile
+// histogram of these Gaussians is built in the same pass (single-GPU forward)
+static int forward_preprocess(const rtg::ViewParams &vp, int32_t p_begin, int32_t p_end, int32_t M, const float *means3D,
+                              const float *shs, const float *colors_precomp, const float *opacities, const float *scales,
+                              const float *rotations, const float *cov3D_precomp, const int32_t *tile_mask, const rtg::GeomState &g,
+                              const rtg::BinState &b, int32_t *radii, bool fused_histogram, cudaStream_t s) {
+    // tile_count, tile_fill, tile_touched and vis_count are adjacent (bin_from): one clear
+    cudaError_t e = cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)b.tile_offset - (char *)b.tile_count), s);
+    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward memset: ") + cudaGetErrorString(e));
+    rtg::launch_preprocess_fwd(vp, p_end, M, means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp, tile_mask, g,
+                               radii, fused_histogram ? b.tile_count : nullptr, b.tile_touched, b.vis_count, p_begin, s);
+    return RTG_OK;
+}
+
+// scan -> scatter -> sort -> compositing over the records of all P Gaussians
+static int forward_bin_render(const rtg::ViewParams &vp, int32_t P, const int32_t *tile_mask, const rtg::GeomState &g,
+                              const rtg::ImgState &img, const rtg::BinState &b, int64_t R_cap, float *out_color, float *out_depth,
+                              int32_t *out_hit_color, int32_t *out_hit_depth, float *out_hit_color_weight, float *out_hit_depth_weight,
+                              float *out_T, const int32_t *radii, int32_t *counters, int32_t *counters_host, void *scan_done_event,
+                              cudaStream_t s) {
+    const int T = vp.tiles_x * vp.tiles_y;
+    rtg::launch_tile_scan(b, T, R_cap, counters, counters_host, s);
+    if (scan_done_event) {
+        cudaError_t e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(scan_done_event), s);
+        if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward event: ") + cudaGetErrorString(e));
+    }
+    rtg::launch_scatter(vp, P, g, radii, tile_mask, b, R_cap, counters, s);
+    rtg::launch_tile_sort(b, T, counters, s);
+    rtg::launch_render_fwd(vp, g, b, img, counters, out_color, out_depth, out_hit_color, out_hit_depth, out_hit_color_weight,
+                           out_hit_depth_weight, out_T, s);
+    return RTG_OK;
+}
+
 int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
                       const float *colors_precomp, const float *opacities, const float *scales, const float *rotations,
                       const float *cov3D_precomp, const int32_t *tile_mask, void *geom_ws, void *img_ws, void *bin_ws,
@@ -164,46 +226,84 @@ int rtg_splat_forward(const RtgSplatView *view, int32_t P, int32_t M, const floa
     if (!out_color || !out_depth || !out_hit_color || !out_hit_depth || !out_hit_color_weight || !out_hit_depth_weight || !out_T ||
         !counters || !geom_ws || !img_ws || !bin_ws || !tile_mask)
         return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: NULL output / workspace / tile_mask pointer");
-    if (P > 0) {
-        if (!means3D || !opacities || !radii) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: NULL means3D / opacities / radii");
-        // same exactly-one-of rules as GaussianRasterizer.forward (__init__.py:335-347)
-        if ((shs == nullptr) == (colors_precomp == nullptr))
-            return fail(RTG_ERR_INVALID_ARGUMENT, "Please provide excatly one of either SHs or precomputed colors!");
-        if (((scales == nullptr || rotations == nullptr) && cov3D_precomp == nullptr) ||
-            ((scales != nullptr || rotations != nullptr) && cov3D_precomp != nullptr))
-            return fail(RTG_ERR_INVALID_ARGUMENT,
-                        "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
-        if (shs && (M < (view->sh_degree + 1) * (view->sh_degree + 1) || M > 16))
-            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: M must hold (sh_degree+1)^2 coefficients and be <= 16");
-        if ((((uintptr_t)rotations) & 15) || (M == 16 && (((uintptr_t)shs) & 15)))
-            return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward: rotations / shs must be 16-byte aligned");
-    }
+    rc = validate_inputs("rtg_splat_forward", view, P, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii);
+    if (rc) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const rtg::ViewParams vp = make_view(view);
     const int T = vp.tiles_x * vp.tiles_y;
     rtg::GeomState g = rtg::geom_from(geom_ws, (size_t)P);
     rtg::ImgState img = rtg::img_from(img_ws, (size_t)vp.H * vp.W);
     rtg::BinState b = rtg::bin_from(bin_ws, (size_t)T, (size_t)R_cap);
-
-    // tile_count, tile_fill, tile_touched and vis_count are adjacent (bin_from): one clear
-    cudaError_t e = cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)b.tile_offset - (char *)b.tile_count), s);
-    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward memset: ") + cudaGetErrorString(e));
-    rtg::launch_preprocess_fwd(vp, P, M, means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp, tile_mask, g,
-                               radii, b.tile_count, b.tile_touched, b.vis_count, s);
-    rtg::launch_tile_scan(b, T, R_cap, counters, counters_host, s);
-    if (scan_done_event) {
-        e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(scan_done_event), s);
-        if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward event: ") + cudaGetErrorString(e));
-    }
-    rtg::launch_scatter(vp, P, g, radii, tile_mask, b, R_cap, counters, s);
-    rtg::launch_tile_sort(b, T, counters, s);
-    rtg::launch_render_fwd(vp, g, b, img, counters, out_color, out_depth, out_hit_color, out_hit_depth, out_hit_color_weight,
-                           out_hit_depth_weight, out_T, s);
+    rc = forward_preprocess(vp, 0, P, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, tile_mask, g, b, radii,
+                            true, s);
+    if (rc) return rc;
+    rc = forward_bin_render(vp, P, tile_mask, g, img, b, R_cap, out_color, out_depth, out_hit_color, out_hit_depth, out_hit_color_weight,
+                            out_hit_depth_weight, out_T, radii, counters, counters_host, scan_done_event, s);
+    if (rc) return rc;
     return check_launch("rtg_splat_forward");
 }
 
+int rtg_splat_geom_layout(int32_t P, size_t *splat_offset, size_t *rgb_offset, size_t *hit_offset, size_t *vis_list_offset) {
+    if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_geom_layout: P < 0");
+    rtg::GeomState g = rtg::geom_from(nullptr, (size_t)P);
+    if (splat_offset) *splat_offset = (size_t)reinterpret_cast<char *>(g.splat);
+    if (rgb_offset) *rgb_offset = (size_t)reinterpret_cast<char *>(g.rgb_flags);
+    if (hit_offset) *hit_offset = (size_t)reinterpret_cast<char *>(g.hit);
+    if (vis_list_offset) *vis_list_offset = (size_t)reinterpret_cast<char *>(g.vis_list);
+    return RTG_OK;
+}
+
+int rtg_splat_forward_preprocess(const RtgSplatView *view, int32_t P, int32_t p_begin, int32_t p_end, int32_t M, const float *means3D,
+                                 const float *shs, const float *colors_precomp, const float *opacities, const float *scales,
+                                 const float *rotations, const float *cov3D_precomp, void *geom_ws, void *bin_ws, int64_t R_cap,
+                                 int32_t *radii, void *stream) {
+    int rc = validate_view(view, "rtg_splat_forward_preprocess");
+    if (rc) return rc;
+    if (P < 0 || p_begin < 0 || p_end < p_begin || p_end > P) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward_preprocess: bad range");
+    if (!geom_ws || !bin_ws || (P > 0 && !radii)) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward_preprocess: NULL workspace / radii");
+    rc = validate_inputs("rtg_splat_forward_preprocess", view, p_end - p_begin, M, means3D, shs, colors_precomp, opacities, scales,
+                         rotations, cov3D_precomp, radii);
+    if (rc) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const rtg::ViewParams vp = make_view(view);
+    const int T = vp.tiles_x * vp.tiles_y;
+    rtg::GeomState g = rtg::geom_from(geom_ws, (size_t)P);
+    rtg::BinState b = rtg::bin_from(bin_ws, (size_t)T, (size_t)R_cap);
+    rc = forward_preprocess(vp, p_begin, p_end, M, shift_rows(means3D, p_begin, 3), shift_rows(shs, p_begin, (size_t)3 * M),
+                            shift_rows(colors_precomp, p_begin, 3), shift_rows(opacities, p_begin, 1), shift_rows(scales, p_begin, 3),
+                            shift_rows(rotations, p_begin, 4), shift_rows(cov3D_precomp, p_begin, 6), nullptr, g, b, radii, false, s);
+    if (rc) return rc;
+    return check_launch("rtg_splat_forward_preprocess");
+}
+
+int rtg_splat_forward_render(const RtgSplatView *view, int32_t P, const int32_t *tile_mask, void *geom_ws, void *img_ws, void *bin_ws,
+                             int64_t R_cap, float *out_color, float *out_depth, int32_t *out_hit_color, int32_t *out_hit_depth,
+                             float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, const int32_t *radii,
+                             int32_t *counters, int32_t *counters_host, void *scan_done_event, void *stream) {
+    int rc = validate_view(view, "rtg_splat_forward_render");
+    if (rc) return rc;
+    if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward_render: P < 0");
+    if (!out_color || !out_depth || !out_hit_color || !out_hit_depth || !out_hit_color_weight || !out_hit_depth_weight || !out_T ||
+        !counters || !geom_ws || !img_ws || !bin_ws || !tile_mask || (P > 0 && !radii))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward_render: NULL output / workspace / tile_mask / radii pointer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const rtg::ViewParams vp = make_view(view);
+    const int T = vp.tiles_x * vp.tiles_y;
+    rtg::GeomState g = rtg::geom_from(geom_ws, (size_t)P);
+    rtg::ImgState img = rtg::img_from(img_ws, (size_t)vp.H * vp.W);
+    rtg::BinState b = rtg::bin_from(bin_ws, (size_t)T, (size_t)R_cap);
+    // a re-run after a capacity overflow must start from a clean histogram / cursors (vis_count stays)
+    cudaError_t e = cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)b.vis_count - (char *)b.tile_count), s);
+    if (e != cudaSuccess) return fail(RTG_ERR_CUDA, std::string("rtg_splat_forward_render memset: ") + cudaGetErrorString(e));
+    rtg::launch_tile_histogram(vp, P, g, radii, tile_mask, b, s);
+    rc = forward_bin_render(vp, P, tile_mask, g, img, b, R_cap, out_color, out_depth, out_hit_color, out_hit_depth, out_hit_color_weight,
+                            out_hit_depth_weight, out_T, radii, counters, counters_host, scan_done_event, s);
+    if (rc) return rc;
+    return check_launch("rtg_splat_forward_render");
+}
+
 // phase: 0 = whole backward, 1 = zero-fill + compositing backward (fills the gradient records), 2 = per-Gaussian backward
-static int splat_backward_impl(int phase, const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+static int splat_backward_impl(int phase, int32_t p_begin, int32_t p_end, const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
                        const float *colors_precomp, const float *scales, const float *rotations, const float *cov3D_precomp,
                        const int32_t *radii, const void *geom_ws, const void *img_ws, const void *bin_ws, int64_t R_cap,
                        const int32_t *counters, const float *final_T, const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch,
@@ -211,7 +311,7 @@ static int splat_backward_impl(int phase, const RtgSplatView *view, int32_t P, i
                        float *dL_drotations, float *dL_dcov3D, float *dL_dmeans2D, void *stream) {
     int rc = validate_view(view, "rtg_splat_backward");
     if (rc) return rc;
-    if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: P < 0");
+    if (P < 0 || p_begin < 0 || p_end < p_begin || p_end > P) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_backward: bad P / range");
     if (P == 0) return RTG_OK;
     if (!means3D || !radii || !geom_ws || !img_ws || !bin_ws || !counters || !final_T || !hit_image || !dL_dcolor || !dL_ddepth ||
         !grad2d_scratch || !dL_dmeans3D || !dL_dopacity)
@@ -240,16 +340,22 @@ static int splat_backward_impl(int phase, const RtgSplatView *view, int32_t P, i
         cudaError_t e = ss ? cudaEventRecord(ss->fork, s) : cudaErrorUnknown;
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
         const bool forked = (e == cudaSuccess);
-        rtg::launch_bwd_zero(P, M, shs != nullptr, cov3D_precomp == nullptr, radii, dL_dmeans3D, dL_dsh, dL_dcolors_precomp,
-                             dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dmeans2D, forked ? ss->stream : s);
+        rtg::launch_bwd_zero(p_begin, p_end, M, shs != nullptr, cov3D_precomp == nullptr, radii, shift_rows(dL_dmeans3D, p_begin, 3),
+                             shift_rows(dL_dsh, p_begin, (size_t)3 * M), shift_rows(dL_dcolors_precomp, p_begin, 3),
+                             shift_rows(dL_dopacity, p_begin, 1), shift_rows(dL_dscales, p_begin, 3), shift_rows(dL_drotations, p_begin, 4),
+                             shift_rows(dL_dcov3D, p_begin, 6), shift_rows(dL_dmeans2D, p_begin, 3), forked ? ss->stream : s);
         if (forked) cudaEventRecord(ss->join, ss->stream);
         rtg::launch_render_bwd(vp, g, b, img, counters, final_T, hit_image, dL_dcolor, dL_ddepth, grad2d_scratch, s);
         if (forked) cudaStreamWaitEvent(s, ss->join, 0);  // enqueued after both: the zero-fill still overlaps render_bwd
     }
-    if (phase != 1)
-        rtg::launch_preprocess_bwd(vp, P, M, means3D, scales, rotations, shs, cov3D_precomp, g, b.vis_count, grad2d_scratch,
-                                   dL_dmeans3D, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,
-                                   dL_dmeans2D, s);
+    if (phase != 1)  // walks the compact visible list, which holds only Gaussians of [p_begin, p_end)
+        rtg::launch_preprocess_bwd(vp, p_end - p_begin, M, shift_rows(means3D, p_begin, 3), shift_rows(scales, p_begin, 3),
+                                   shift_rows(rotations, p_begin, 4), shift_rows(shs, p_begin, (size_t)3 * M),
+                                   shift_rows(cov3D_precomp, p_begin, 6), g, b.vis_count, grad2d_scratch,
+                                   shift_rows(dL_dmeans3D, p_begin, 3), shift_rows(dL_dsh, p_begin, (size_t)3 * M),
+                                   shift_rows(dL_dcolors_precomp, p_begin, 3), shift_rows(dL_dopacity, p_begin, 1),
+                                   shift_rows(dL_dscales, p_begin, 3), shift_rows(dL_drotations, p_begin, 4),
+                                   shift_rows(dL_dcov3D, p_begin, 6), shift_rows(dL_dmeans2D, p_begin, 3), s);
     return check_launch("rtg_splat_backward");
 }
 
@@ -264,9 +370,15 @@ static int splat_backward_impl(int phase, const RtgSplatView *view, int32_t P, i
     view, P, M, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii, geom_ws, img_ws, bin_ws, R_cap, counters,  \
         final_T, hit_image, dL_dcolor, dL_ddepth, grad2d_scratch, dL_dmeans3D, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, \
         dL_drotations, dL_dcov3D, dL_dmeans2D, stream
-int rtg_splat_backward(RTG_BWD_PARAMS) { return splat_backward_impl(0, RTG_BWD_ARGS); }
-int rtg_splat_backward_render(RTG_BWD_PARAMS) { return splat_backward_impl(1, RTG_BWD_ARGS); }
-int rtg_splat_backward_finish(RTG_BWD_PARAMS) { return splat_backward_impl(2, RTG_BWD_ARGS); }
+int rtg_splat_backward(RTG_BWD_PARAMS) { return splat_backward_impl(0, 0, P, RTG_BWD_ARGS); }
+int rtg_splat_backward_render(RTG_BWD_PARAMS) { return splat_backward_impl(1, 0, P, RTG_BWD_ARGS); }
+int rtg_splat_backward_finish(RTG_BWD_PARAMS) { return splat_backward_impl(2, 0, P, RTG_BWD_ARGS); }
+int rtg_splat_backward_render_shard(int32_t p_begin, int32_t p_end, RTG_BWD_PARAMS) {
+    return splat_backward_impl(1, p_begin, p_end, RTG_BWD_ARGS);
+}
+int rtg_splat_backward_finish_shard(int32_t p_begin, int32_t p_end, RTG_BWD_PARAMS) {
+    return splat_backward_impl(2, p_begin, p_end, RTG_BWD_ARGS);
+}
 
 int rtg_splat_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix, uint8_t *present,
                            void *stream) {

@@ -7,16 +7,19 @@ namespace rtg {
 void launch_preprocess_fwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
                            const float *opac, const float *shs, const float *colors_precomp, const float *cov3D_precomp,
                            const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, uint32_t *tile_touched,
-                           uint32_t *vis_count, cudaStream_t s);
+                           uint32_t *vis_count, int p_begin, cudaStream_t s);
 void launch_mark_visible(int P, const float *means, const float *view, const float *proj, uint8_t *present, cudaStream_t s);
-void launch_bwd_zero(int P, int M, bool has_sh, bool has_sr, const int *radii, float *dL_dmeans, float *dL_dsh, float *dL_dcolors,
-                     float *dL_dopacity, float *dL_dscales, float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s);
+void launch_bwd_zero(int p_begin, int P, int M, bool has_sh, bool has_sr, const int *radii, float *dL_dmeans, float *dL_dsh,
+                     float *dL_dcolors, float *dL_dopacity, float *dL_dscales, float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D,
+                     cudaStream_t s);
 void launch_preprocess_bwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
                            const float *shs, const float *cov3D_precomp, const GeomState &g, const uint32_t *vis_count, float *rec,
                            float *dL_dmeans, float *dL_dsh, float *dL_dcolors, float *dL_dopacity, float *dL_dscales, float *dL_drot,
                            float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s);
 
 // binning.cu
+void launch_tile_histogram(const ViewParams &vp, int P, const GeomState &g, const int *radii, const int *tile_mask, const BinState &b,
+                           cudaStream_t s);
 void launch_tile_scan(const BinState &b, int T, int64_t R_cap, int32_t *counters, int32_t *counters_host, cudaStream_t s);
 void launch_scatter(const ViewParams &vp, int P, const GeomState &g, const int *radii, const int *tile_mask, const BinState &b,
                     int64_t R_cap, const int32_t *counters, cudaStream_t s);

@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(co
                                                              const float *__restrict__ cov3D_precomp,
                                                              const int *__restrict__ tile_mask, GeomState g,
                                                              int *__restrict__ radii, uint32_t *__restrict__ tile_count,
-                                                             uint32_t *__restrict__ tile_touched, uint32_t *__restrict__ vis_count) {
+                                                             uint32_t *__restrict__ tile_touched, uint32_t *__restrict__ vis_count,
+                                                             const int p_begin) {
     __shared__ float s_m[40];
     __shared__ uint32_t s_excl[8][32], s_rect[8][32];
     __shared__ float4 s_ga[8][32], s_gb[8][32];
@@ -256,7 +257,9 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(co
     else if (threadIdx.x < 32) s_m[threadIdx.x] = vp.proj[threadIdx.x - 16];
     else if (threadIdx.x < 35) s_m[threadIdx.x] = vp.campos[threadIdx.x - 32];
     __syncthreads();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // Gaussians [p_begin, P) of the map: the whole map, or the slice a rank owns (the parameter pointers are then
+    // shifted so that they can be indexed with the global id; the records are always indexed with the global id)
+    const int idx = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
     SplatTiles st;
@@ -277,6 +280,7 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(co
             if (valid) g.vis_list[basep + __popc(vb & ((1u << lane) - 1u))] = (uint32_t)idx;
         }
     }
+    if (tile_count == nullptr) return;  // Gaussian-sharded forward: the histogram runs after the exchange of the records
     const int npairs = valid ? (st.x1 - st.x0) * (st.y1 - st.y0) : 0;
     const int incl = warp_incl_scan(npairs, lane);
     const int total = __shfl_sync(0xffffffffu, incl, 31);
@@ -614,9 +618,9 @@ __device__ __forceinline__ void bwd_visible(const ViewParams &vp, const int idx,
 // Zero gradients for the culled Gaussians (the reference zero-fills every gradient tensor first,
 // rasterize_points.cu:195-203). Pure streaming stores that depend on the forward only, so the C ABI runs this kernel
 // on a side stream, concurrently with the compute-bound render backward.
-__global__ void __launch_bounds__(256) bwd_zero_kernel(const int P, const int M, const bool has_sh, const bool has_sr,
+__global__ void __launch_bounds__(256) bwd_zero_kernel(const int p_begin, const int P, const int M, const bool has_sh, const bool has_sr,
                                                        const int *__restrict__ radii, const BwdOut o) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const bool culled = idx < P && !(radii[idx] > 0);
     const bool coop_sh = has_sh && (M == 16);
     if (coop_sh) {
@@ -661,11 +665,12 @@ __global__ void __launch_bounds__(PBWD_THREADS, PBWD_MIN_BLOCKS) preprocess_bwd_
 void launch_preprocess_fwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,
                            const float *opac, const float *shs, const float *colors_precomp, const float *cov3D_precomp,
                            const int *tile_mask, const GeomState &g, int *radii, uint32_t *tile_count, uint32_t *tile_touched,
-                           uint32_t *vis_count, cudaStream_t s) {
-    if (P <= 0) return;
+                           uint32_t *vis_count, int p_begin, cudaStream_t s) {
+    if (P - p_begin <= 0) return;
     ProfScope ps(K_PREPROCESS_FWD, s);
-    preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, opac, shs, colors_precomp, cov3D_precomp,
-                                                          tile_mask, g, radii, tile_count, tile_touched, vis_count);
+    preprocess_fwd_kernel<<<(P - p_begin + 255) / 256, 256, 0, s>>>(vp, P, M, means, scales, rots, opac, shs, colors_precomp,
+                                                                    cov3D_precomp, tile_mask, g, radii, tile_count, tile_touched,
+                                                                    vis_count, p_begin);
 }
 
 void launch_mark_visible(int P, const float *means, const float *view, const float *proj, uint8_t *present, cudaStream_t s) {
@@ -673,12 +678,13 @@ void launch_mark_visible(int P, const float *means, const float *view, const flo
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means, view, proj, present);
 }
 
-void launch_bwd_zero(int P, int M, bool has_sh, bool has_sr, const int *radii, float *dL_dmeans, float *dL_dsh, float *dL_dcolors,
-                     float *dL_dopacity, float *dL_dscales, float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D, cudaStream_t s) {
-    if (P <= 0) return;
+void launch_bwd_zero(int p_begin, int P, int M, bool has_sh, bool has_sr, const int *radii, float *dL_dmeans, float *dL_dsh,
+                     float *dL_dcolors, float *dL_dopacity, float *dL_dscales, float *dL_drot, float *dL_dcov3D, float *dL_dmeans2D,
+                     cudaStream_t s) {
+    if (P - p_begin <= 0) return;
     ProfScope ps(K_BWD_ZERO, s);
     BwdOut o{dL_dmeans, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drot, dL_dcov3D, dL_dmeans2D};
-    bwd_zero_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, M, has_sh, has_sr, radii, o);
+    bwd_zero_kernel<<<(P - p_begin + 255) / 256, 256, 0, s>>>(p_begin, P, M, has_sh, has_sr, radii, o);
 }
 
 void launch_preprocess_bwd(const ViewParams &vp, int P, int M, const float *means, const float *scales, const float *rots,

@@ -175,3 +175,202 @@ def assert_replicas_equal(tensors: Sequence[torch.Tensor], atol: float = 0.0) ->
         dist.broadcast(ref, src=0)
         if not torch.allclose(ref, t, atol=atol, rtol=0):
             raise AssertionError(f"rank {rank()} diverged from rank 0 (max abs diff {(ref - t).abs().max().item():.3e})")
+
+
+# ----------------------------------------------------------------------------- Gaussian-sharded rendering
+def shard_range(P: int, world_size: int, r: int):
+    """[p_begin, p_end) of the map owned by rank r: equal slices (the exchanges are all-gather / reduce-scatter of equal
+    pieces, so P must be a multiple of the world size: pad the map with culled Gaussians, e.g. behind the camera)."""
+    if P % world_size != 0:
+        raise ValueError(f"P = {P} must be a multiple of the world size {world_size} (pad the map)")
+    n = P // world_size
+    return r * n, (r + 1) * n
+
+
+class _Collectives:
+    """all-gather of equal row slices / reduce-scatter of equal row slices; over torch.distributed when a group is up,
+    emulated in-process for the single-GPU tests (`peers`: the other emulated ranks share the buffers)."""
+
+    def __init__(self, world_size, r):
+        self.world, self.rank = world_size, r
+
+    def all_gather_rows(self, full: torch.Tensor):
+        """`full` (P, ...) with this rank's slice filled in: on return every slice holds its owner's data."""
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            return
+        n = full.shape[0] // self.world
+        mine = full[self.rank * n:(self.rank + 1) * n]
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(full, mine)  # in place: `mine` is this rank's slice of `full`
+        else:  # gloo (CPU tests): list form
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine.contiguous())
+            for k, p in enumerate(parts):
+                full[k * n:(k + 1) * n].copy_(p)
+
+    def reduce_scatter_rows(self, full: torch.Tensor, out: torch.Tensor):
+        """out (P / world, ...) = sum over ranks of their `full`[own slice of this rank]."""
+        n = full.shape[0] // self.world
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            out.copy_(full[self.rank * n:(self.rank + 1) * n])
+            return
+        if dist.get_backend() == "nccl":
+            dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM)
+        else:
+            tmp = full.clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+            out.copy_(tmp[self.rank * n:(self.rank + 1) * n])
+
+
+class GaussianShard:
+    """One rank's part of a Gaussian-sharded frame (BASELINE configs[4]).
+
+    The rank owns the parameters (and gradients, optimizer state) of the Gaussians [p_begin, p_end) and a subset of the
+    tiles (`TileShard`). Forward: preprocess of the owned Gaussians -> all-gather of the per-Gaussian records (80 B +
+    radius per Gaussian) -> binning + compositing of the owned tiles against all records. Backward: compositing backward
+    of the owned tiles -> reduce-scatter of the 64-byte gradient records to the owners -> per-Gaussian backward of the
+    owned Gaussians. No parameter is ever replicated; the only full-size buffers are the records.
+
+        sh = GaussianShard(P, H, W, device)
+        out = sh.forward(raster_settings, means3D, opacities, shs, scales, rotations)      # owned rows
+        grads = sh.backward(dL_dcolor, dL_ddepth)                                           # owned rows
+    """
+
+    def __init__(self, P: int, H: int, W: int, device, world_size: int | None = None, r: int | None = None, tile_weights=None,
+                 collectives=None):
+        from . import _lib
+        self.P, self.H, self.W = P, H, W
+        self.world = world() if world_size is None else world_size
+        self.rank = rank() if r is None else r
+        self.device = torch.device(device)
+        self.p_begin, self.p_end = shard_range(P, self.world, self.rank)
+        self.tiles = TileShard(H, W, self.world, self.rank, weights=tile_weights, device=self.device)
+        self.coll = collectives if collectives is not None else _Collectives(self.world, self.rank)
+        self.r_cap = 1 << 16
+        self._lib = _lib
+        L = _lib.lib()
+        import ctypes as C
+        offs = [C.c_size_t() for _ in range(4)]
+        _lib.check(L.rtg_splat_geom_layout(P, *[C.byref(o) for o in offs]), "rtg_splat_geom_layout")
+        self._geom_off = [o.value for o in offs]
+        gb, ib, bb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(L.rtg_splat_workspace_bytes(P, H, W, self.r_cap, C.byref(gb), C.byref(ib), C.byref(bb)), "rtg_splat_workspace_bytes")
+        self.geom = torch.empty(gb.value, dtype=torch.uint8, device=self.device)
+        self.img = torch.empty(ib.value, dtype=torch.uint8, device=self.device)
+        self.bin = None
+        self.radii = torch.zeros(P, dtype=torch.int32, device=self.device)
+        self.rec_full = torch.zeros((P, 16), dtype=torch.float32, device=self.device)   # gradient records, zero between uses
+        self.rec_own = torch.empty((self.p_end - self.p_begin, 16), dtype=torch.float32, device=self.device)
+        self.counters = torch.zeros(_lib.RTG_CNT_WORDS, dtype=torch.int32, device=self.device)
+        self.pinned = torch.zeros(_lib.RTG_CNT_WORDS, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event() if self.device.type == "cuda" else None
+        if self.event is not None:
+            with torch.cuda.device(self.device):
+                self.event.record()
+        self._saved = None
+
+    # typed views of the record arrays inside the geometry workspace (what the all-gather moves)
+    def _record_views(self):
+        P = self.P
+        o_splat, o_rgb, o_hit, _ = self._geom_off
+        g = self.geom
+        return [g[o_splat:o_splat + 32 * P].view(torch.float32).view(P, 8), g[o_rgb:o_rgb + 16 * P].view(torch.float32).view(P, 4),
+                g[o_hit:o_hit + 32 * P].view(torch.float32).view(P, 8)]
+
+    def exchange_bytes(self):
+        """bytes received per rank and step: records all-gather + gradient-record reduce-scatter"""
+        frac = (self.world - 1) / self.world
+        return {"all_gather": int((32 + 16 + 32 + 4) * self.P * frac), "reduce_scatter": int(64 * self.P * frac)}
+
+    def forward(self, rs, means3D, opacities, shs, scales, rotations, tile_mask=None, staged=False):
+        import ctypes as C
+        from .rasterizer import _make_view, _f32_cuda
+        L, lib = self._lib.lib(), self._lib
+        dev = self.device
+        n = self.p_end - self.p_begin
+        for t, cols in ((means3D, 3), (opacities, 1), (scales, 3), (rotations, 4)):
+            if t.shape[0] != n:
+                raise ValueError(f"parameter tensors must hold the {n} owned rows")
+        means3D, opacities, shs, scales, rotations = (_f32_cuda(t, nm, dev) for t, nm in (
+            (means3D, "means3D"), (opacities, "opacities"), (shs, "shs"), (scales, "scales"), (rotations, "rotations")))
+        M = shs.shape[1]
+        view, keep = _make_view(rs, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        H, W, P = self.H, self.W, self.P
+        mask = self.tiles.mask if tile_mask is None else (self.tiles.mask * (tile_mask.to(dev) != 0).to(torch.int32)).contiguous()
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        outs = [torch.empty((3, H, W), **f32), torch.empty((1, H, W), **f32), torch.empty((1, H, W), **i32), torch.empty((1, H, W), **i32),
+                torch.empty((1, H, W), **f32), torch.empty((1, H, W), **f32), torch.empty((1, H, W), **f32)]
+        p = lambda t: C.c_void_p(t.data_ptr())
+        gb, ib, bb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+
+        def preprocess():
+            lib.check(L.rtg_splat_workspace_bytes(P, H, W, self.r_cap, C.byref(gb), C.byref(ib), C.byref(bb)), "rtg_splat_workspace_bytes")
+            if self.bin is None or self.bin.numel() < bb.value:
+                self.bin = torch.empty(bb.value, dtype=torch.uint8, device=dev)
+            lib.check(L.rtg_splat_forward_preprocess(C.byref(view), P, self.p_begin, self.p_end, M, p(means3D), p(shs), None, p(opacities),
+                                                     p(scales), p(rotations), None, p(self.geom), p(self.bin), self.r_cap,
+                                                     p(self.radii), C.c_void_p(stream)), "rtg_splat_forward_preprocess")
+
+        def render():
+            """False if the binning buffer was too small (the caller grows it, preprocesses and exchanges again: the
+            visible-list counter lives in the binning workspace, which moves)."""
+            lib.check(L.rtg_splat_forward_render(C.byref(view), P, p(mask), p(self.geom), p(self.img), p(self.bin), self.r_cap,
+                                                 *[p(o) for o in outs], p(self.radii), p(self.counters), C.c_void_p(self.pinned.data_ptr()),
+                                                 C.c_void_p(self.event.cuda_event), C.c_void_p(stream)), "rtg_splat_forward_render")
+            self.event.synchronize()  # the scan kernel's counters (the compositing is still running)
+            self.num_rendered, overflow = int(self.pinned[0]), int(self.pinned[2])
+            if overflow:
+                self.r_cap = int(self.num_rendered * 1.5) + 4096
+                return False
+            self.r_cap = max(self.r_cap, int(self.num_rendered * 1.25) + 4096)
+            return True
+
+        self._saved = (view, keep, M, means3D, shs, scales, rotations, outs, mask)
+        names = ("color", "depth", "hit_color", "hit_depth", "hit_color_weight", "hit_depth_weight", "T_map")
+        res = dict(zip(names, outs))
+        res["radii"] = self.radii
+        if staged:  # the caller performs the exchange itself (single-process emulation of several ranks in the tests)
+            return res, preprocess, render
+        while True:
+            preprocess()
+            self.exchange_records_forward()
+            if render():
+                return res
+
+    def exchange_records_forward(self):
+        for v in self._record_views():
+            self.coll.all_gather_rows(v)
+        self.coll.all_gather_rows(self.radii)
+
+    def backward(self, dL_dcolor, dL_ddepth, staged=False):
+        import ctypes as C
+        from .rasterizer import _f32_cuda
+        L, lib = self._lib.lib(), self._lib
+        dev = self.device
+        view, keep, M, means3D, shs, scales, rotations, outs, mask = self._saved
+        n = self.p_end - self.p_begin
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = dict(means3D=torch.empty((n, 3), **f32), shs=torch.empty((n, M, 3), **f32), opacities=torch.empty((n, 1), **f32),
+                 scales=torch.empty((n, 3), **f32), rotations=torch.empty((n, 4), **f32))
+        gc, gd = _f32_cuda(dL_dcolor, "dL_dcolor", dev), _f32_cuda(dL_ddepth, "dL_ddepth", dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+
+        def args(rec_ptr):
+            return (self.p_begin, self.p_end, C.byref(view), self.P, M, p(means3D), p(shs), None, p(scales), p(rotations), None,
+                    p(self.radii), p(self.geom), p(self.img), p(self.bin), self.r_cap, p(self.counters), p(outs[6]), p(outs[3]), p(gc), p(gd),
+                    rec_ptr, p(g["means3D"]), p(g["shs"]), None, p(g["opacities"]), p(g["scales"]), p(g["rotations"]), None, None, stream)
+        def render():
+            lib.check(L.rtg_splat_backward_render_shard(*args(p(self.rec_full))), "rtg_splat_backward_render_shard")
+
+        def finish():
+            self.rec_full.zero_()
+            lib.check(L.rtg_splat_backward_finish_shard(*args(C.c_void_p(self.rec_own.data_ptr() - self.p_begin * 64))),
+                      "rtg_splat_backward_finish_shard")
+            return g
+        if staged:
+            return render, finish
+        render()
+        self.coll.reduce_scatter_rows(self.rec_full, self.rec_own)
+        return finish()

@@ -179,3 +179,55 @@ def test_tile_shard_tables():
     # single process: gather is the identity on owned pixels
     img = torch.rand(3, H, W)
     assert torch.equal(parallel.TileShard(H, W, 1, 0).gather(img), img)
+
+
+# ---------------------------------------------------------------------------------------------- Gaussian sharding
+def _gshard_worker(rank, world, port, q):
+    """The two exchanges of a Gaussian-sharded frame (parallel.GaussianShard) over gloo: all-gather of equal row slices in
+    place, reduce-scatter of equal row slices."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P = 12
+        a, b = parallel.shard_range(P, world, rank)
+        coll = parallel._Collectives(world, rank)
+        rec = torch.full((P, 8), float("nan"))
+        rec[a:b] = torch.arange(a, b, dtype=torch.float32)[:, None] * 10 + torch.arange(8, dtype=torch.float32)
+        coll.all_gather_rows(rec)
+        radii = torch.zeros(P, dtype=torch.int32)
+        radii[a:b] = torch.arange(a, b, dtype=torch.int32) + 1
+        coll.all_gather_rows(radii)
+        partial = torch.full((P, 16), float(rank + 1))
+        own = torch.empty((b - a, 16))
+        coll.reduce_scatter_rows(partial, own)
+        q.put((rank, rec.numpy(), radii.numpy(), own.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gaussian_shard_exchanges():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gshard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(12, dtype=np.float32)[:, None] * 10 + np.arange(8, dtype=np.float32)
+    for r in res:
+        assert np.array_equal(r[1], want) and np.array_equal(r[2], np.arange(12) + 1)
+        assert r[3].shape == (6, 16) and np.all(r[3] == 3.0)  # 1 + 2
+    assert parallel.shard_range(12, 3, 2) == (8, 12)
+    with pytest.raises(ValueError):
+        parallel.shard_range(10, 4, 0)
+    # single process: the exchanges degenerate to the identity / a copy
+    c = parallel._Collectives(1, 0)
+    x = torch.arange(6.0).view(3, 2)
+    y = torch.empty(3, 2)
+    c.all_gather_rows(x)
+    c.reduce_scatter_rows(x, y)
+    assert torch.equal(x, y)

@@ -368,3 +368,59 @@ def test_two_phase_backward_with_record_exchange(cuda_device):
     for k in full["grads"]:
         assert helpers.rel_err(same["grads"][k], full["grads"][k]) < 1e-5, k
         assert helpers.rel_err(again["grads"][k], full["grads"][k]) < 1e-5, k   # scratch left clean
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 3])
+def test_gaussian_sharded_frame_matches_unsharded(cuda_device, world):
+    """SURVEY 8(e) / BASELINE configs[4]: Gaussians AND tiles sharded over ranks (parallel.GaussianShard). Emulated on one
+    GPU by running the ranks' stages in lock step and doing the two exchanges by hand (all-gather of the per-Gaussian
+    records = copying every owner's slice to every rank; reduce-scatter of the gradient records = summing the ranks'
+    record buffers and handing each owner its slice). The union of the image pieces is bit-identical to the unsharded
+    render, the owners' gradients equal the rows of the unsharded gradient."""
+    from rtg_slam_b200.parallel import GaussianShard
+    cam = scene.make_camera("replica")
+    P = 30_000
+    g = scene.surfel_room(P, seed=23)
+    grads = scene.upstream_grads(cam, seed=5)
+    full = helpers.run_ours(cam, g, cuda_device, grads=grads)
+    rs = helpers.make_settings(cam, cuda_device)
+    t = helpers.to_torch(g, cuda_device)
+    shards = [GaussianShard(P, cam.height, cam.width, cuda_device, world_size=world, r=r) for r in range(world)]
+    staged = []
+    for sh in shards:
+        a, b = sh.p_begin, sh.p_end
+        staged.append(sh.forward(rs, t["xyz"][a:b], t["opacity"][a:b], t["shs"][a:b], t["scales"][a:b], t["rotations"][a:b], staged=True))
+    for _ in range(2):  # second pass: the first one may have overflowed the initial binning capacity
+        for (_, pre, _) in staged:
+            pre()
+        for sh in shards:  # all-gather by hand
+            for dst in shards:
+                if dst is sh:
+                    continue
+                for vs, vd in zip(sh._record_views(), dst._record_views()):
+                    vd[sh.p_begin:sh.p_end].copy_(vs[sh.p_begin:sh.p_end])
+                dst.radii[sh.p_begin:sh.p_end].copy_(sh.radii[sh.p_begin:sh.p_end])
+        ok = [ren() for (_, _, ren) in staged]
+        if all(ok):
+            break
+    assert all(ok)
+    assert np.array_equal(shards[0].radii.cpu().numpy(), full["radii"])
+    for k in ("color", "depth", "hit_color", "hit_depth", "hit_color_weight", "hit_depth_weight", "T_map"):
+        acc = np.zeros_like(full[k])
+        for sh, (res, _, _) in zip(shards, staged):
+            acc = np.where(sh.tiles.pixel_mask.cpu().numpy()[None], res[k].cpu().numpy(), acc)
+        assert np.array_equal(acc, full[k]), k
+    gc, gd = torch.from_numpy(grads[0]).to(cuda_device), torch.from_numpy(grads[1]).to(cuda_device)
+    stages = [sh.backward(gc, gd, staged=True) for sh in shards]
+    for ren, _ in stages:
+        ren()
+    total = sum(sh.rec_full for sh in shards)  # reduce ...
+    for sh in shards:                           # ... scatter
+        sh.rec_own.copy_(total[sh.p_begin:sh.p_end])
+    for sh, (_, fin) in zip(shards, stages):
+        own = fin()
+        for k in GRADS:
+            want = full["grads"][k][sh.p_begin:sh.p_end]
+            assert helpers.rel_err(own[k].cpu().numpy().reshape(want.shape), want) < 1e-4, (k, sh.rank)
+        assert float(sh.rec_full.abs().max()) == 0.0  # the record buffer is clean for the next step
