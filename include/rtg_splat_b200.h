@@ -262,6 +262,17 @@ int rtg_loss_l1(const float *render, const float *depth, const int32_t *depth_in
                 const uint8_t *render_mask, int32_t H, int32_t W, int32_t gt_channels_last, float color_weight, float depth_weight,
                 float depth_error_max, float *dL_dcolor, float *dL_ddepth, float *loss_out, void *ws, void *stream);
 
+/* The same loss with the cosine normal term of Mapping.loss_update (mapper.py:433-442):
+ *   normal = mean of 1 - cosine_similarity(render_normal, gt_normal) over pixels with render_mask, depth_index != -1 and
+ *            gt_normal != 0,  loss = color_weight*colour + depth_weight*depth + normal_weight*normal.
+ * render_normal (3,H,W) is Renderer.render's "normal"; gt_normal (H,W,3); dL_dnormal (3,H,W). With normal_weight == 0 the
+ * three normal pointers may be NULL. loss_out: 8 device floats {loss, colour, depth, n_depth, normal, n_normal, 0, 0}:
+ * everything Mapping.loss_update reports (mapper.py:459-466) in one buffer, one read-back instead of six .item() calls. */
+int rtg_loss_mapping(const float *render, const float *depth, const float *render_normal, const int32_t *depth_index,
+                     const float *gt_color, const float *gt_depth, const float *gt_normal, const uint8_t *render_mask, int32_t H, int32_t W,
+                     int32_t gt_channels_last, float color_weight, float depth_weight, float normal_weight, float depth_error_max,
+                     float *dL_dcolor, float *dL_ddepth, float *dL_dnormal, float *loss_out, void *ws, void *stream);
+
 /* render_normal of Renderer.render (SLAM/render.py:130-133): out (3,H,W) = normal[depth_index] where the index is
  * > -1, zeros elsewhere; normal is (P,3). */
 int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream);

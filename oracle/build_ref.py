@@ -63,26 +63,43 @@ def build_cuda_utils():
 
 
 def build_simple_knn():
-    """submodules/simple-knn (distCUDA2): same recipe; gcc 13 additionally needs <cfloat> / <climits> for
-    FLT_MAX / INT_MAX (simple_knn.cu:90,176-177). Module `_C` kept under oracle/_ref/simple_knn/."""
+    """submodules/simple-knn (distCUDA2), compiled from its three sources where they lie with the flags of
+    its own setup.py, plus <cfloat> / <climits> (gcc 13: FLT_MAX / INT_MAX, simple_knn.cu:90,176-177) and a distinct module
+    name: cuda_utils and simple-knn both call their extension `_C`, and two single-phase extension modules of the same
+    name cannot be loaded side by side in one test process. Output: oracle/_ref/simple_knn/_C_simple_knn*.so."""
+    import sysconfig
+    from torch.utils import cpp_extension as ce
     ref = "/root/reference/submodules/simple-knn"
     out = os.path.join(OUT, "simple_knn")
     if not os.path.isdir(ref):
         return 0
-    if glob.glob(os.path.join(out, "_C*.so")) and "--force" not in sys.argv:
+    if glob.glob(os.path.join(out, "_C_simple_knn*.so")) and "--force" not in sys.argv:
         print("oracle/_ref/simple_knn already built")
         return 0
     os.makedirs(out, exist_ok=True)
     tmp = "/tmp/rtg_refbuild_simple_knn"
     shutil.rmtree(tmp, ignore_errors=True)
-    shutil.copytree(ref, tmp)
-    env = dict(os.environ, NVCC_APPEND_FLAGS="-include cstdint -include cfloat -include climits", TORCH_CUDA_ARCH_LIST="10.0",
-               MAX_JOBS="8")
-    subprocess.check_call([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=tmp, env=env)
-    so = glob.glob(os.path.join(tmp, "simple_knn", "_C*.so"))
-    assert so, "simple-knn build produced no extension"
-    shutil.copy(so[0], out)
-    print("built", os.path.join(out, os.path.basename(so[0])))
+    os.makedirs(tmp)
+    name = "_C_simple_knn"
+    inc = [f"-I{p}" for p in ce.include_paths("cuda")] + [f"-I{sysconfig.get_paths()['include']}"]
+    defs = [f"-DTORCH_EXTENSION_NAME={name}", "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1"]
+    objs = []
+    for src in ("spatial.cu", "simple_knn.cu"):
+        o = os.path.join(tmp, src + ".o")
+        subprocess.check_call(["nvcc", "-c", os.path.join(ref, src), "-o", o, "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+                               "-gencode", "arch=compute_100,code=sm_100", "-Xcompiler", "-fPIC", "-include", "cstdint", "-include",
+                               "cfloat", "-include", "climits", *defs, *inc])
+        objs.append(o)
+    o = os.path.join(tmp, "ext.o")
+    subprocess.check_call(["g++", "-c", os.path.join(ref, "ext.cpp"), "-o", o, "-O2", "-std=c++17", "-fPIC", *defs, *inc])
+    objs.append(o)
+    so = os.path.join(out, name + sysconfig.get_config_var("EXT_SUFFIX"))
+    libdirs = [f"-L{p}" for p in ce.library_paths("cuda")]
+    subprocess.check_call(["g++", "-shared", "-o", so, *objs, *libdirs, "-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10_cuda",
+                           "-ltorch_cuda", "-lcudart"])
+    for old in glob.glob(os.path.join(out, "_C.*.so")):
+        os.remove(old)
+    print("built", so)
     return 0
 
 

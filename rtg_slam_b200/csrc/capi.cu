@@ -26,6 +26,10 @@ size_t loss_ws_bytes();
 void launch_loss_l1(const float *render, const float *depth, const int *depth_index, const float *gt_color, const float *gt_depth,
                     const uint8_t *mask, int H, int W, int channels_last, float color_weight, float depth_weight,
                     float depth_error_max, float *dL_dcolor, float *dL_ddepth, float *loss_out, void *ws, cudaStream_t s);
+void launch_loss_mapping(const float *render, const float *depth, const float *render_normal, const int *depth_index,
+                         const float *gt_color, const float *gt_depth, const float *gt_normal, const uint8_t *mask, int H, int W,
+                         int channels_last, float color_weight, float depth_weight, float normal_weight, float depth_error_max,
+                         float *dL_dcolor, float *dL_ddepth, float *dL_dnormal, float *loss_out, void *ws, cudaStream_t s);
 void launch_normal_map(const float *normal, const int *depth_index, int H, int W, float *out, cudaStream_t s);
 void launch_icp_fill(float *render_depth, const float *frame_depth, const float *rn, const float *fn, int H, int W, float dthr,
                      float nthr, cudaStream_t s);
@@ -502,6 +506,20 @@ int rtg_loss_l1(const float *render, const float *depth, const int32_t *depth_in
     rtg::launch_loss_l1(render, depth, depth_index, gt_color, gt_depth, render_mask, H, W, gt_channels_last, color_weight, depth_weight,
                         depth_error_max, dL_dcolor, dL_ddepth, loss_out, ws, reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_loss_l1");
+}
+
+int rtg_loss_mapping(const float *render, const float *depth, const float *render_normal, const int32_t *depth_index,
+                     const float *gt_color, const float *gt_depth, const float *gt_normal, const uint8_t *render_mask, int32_t H, int32_t W,
+                     int32_t gt_channels_last, float color_weight, float depth_weight, float normal_weight, float depth_error_max,
+                     float *dL_dcolor, float *dL_ddepth, float *dL_dnormal, float *loss_out, void *ws, void *stream) {
+    if (!render || !depth || !depth_index || !gt_color || !gt_depth || !dL_dcolor || !dL_ddepth || !loss_out || !ws || H <= 0 || W <= 0)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_loss_mapping: bad arguments");
+    if (normal_weight > 0.f && (!render_normal || !gt_normal || !dL_dnormal))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_loss_mapping: normal_weight > 0 needs render_normal, gt_normal and dL_dnormal");
+    rtg::launch_loss_mapping(render, depth, render_normal, depth_index, gt_color, gt_depth, gt_normal, render_mask, H, W, gt_channels_last,
+                             color_weight, depth_weight, normal_weight, depth_error_max, dL_dcolor, dL_ddepth, dL_dnormal, loss_out, ws,
+                             reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_loss_mapping");
 }
 
 int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream) {

@@ -54,8 +54,9 @@ def shard_frames(n_frames: int, world_size: int | None = None, r: int | None = N
 
 
 class FlatGrads:
-    """One contiguous fp32 buffer holding all per-Gaussian gradient tensors, with typed views into it. The
-    rasterizer backward writes into the views; `allreduce` then needs a single collective and no packing."""
+    """One contiguous fp32 buffer holding all per-Gaussian gradient tensors, with typed views into it. Inside
+    `rasterizer.grad_buffers(flat.views)` the rasterizer backward writes straight into the views; `allreduce` then needs
+    a single collective and no packing (`accumulate` is the packing path for gradients produced elsewhere)."""
 
     def __init__(self, P: int, device, sh_coeffs: int = 16):
         self.P = P
@@ -79,10 +80,12 @@ class FlatGrads:
         return self
 
     def allreduce(self, average: bool = False, async_op: bool = False):
+        if average and async_op:
+            raise ValueError("FlatGrads.allreduce: average=True needs the result, i.e. async_op=False (divide after wait())")
         if world() == 1:
             return None
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
-        if average and not async_op:
+        if average:
             self.flat.div_(world())
         return work
 

@@ -319,12 +319,23 @@ class _RasterizeGaussians(torch.autograd.Function):
         stream = torch.cuda.current_stream(device).cuda_stream
         st = _state(device)
 
-        g_means = torch.empty((P, 3), **f32)
-        g_opac = torch.empty((P, 1), **f32)
-        g_sh = torch.empty((P, M, 3), **f32) if sh is not None else None
+        buf = _GRAD_BUFFERS[0]
+
+        def out(name, shape):
+            """Gradient tensor: a fresh allocation, or -- inside `grad_buffers(...)` -- a fresh alias of the caller's buffer
+            (e.g. a view into parallel.FlatGrads: the kernels write straight into the all-reduce buffer, no packing)."""
+            if buf is not None and name in buf:
+                t = buf[name]
+                if t.numel() != int(torch.Size(shape).numel()) or t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+                    raise ValueError(f"grad buffer '{name}' must be a contiguous float32 tensor of {tuple(shape)} on {device}")
+                return t.view(shape)
+            return torch.empty(shape, **f32)
+        g_means = out("means3D", (P, 3))
+        g_opac = out("opacities", (P, 1))
+        g_sh = out("shs", (P, M, 3)) if sh is not None else None
         g_colors = torch.empty((P, 3), **f32) if colors_precomp is not None else None
-        g_scales = torch.empty((P, 3), **f32) if scales is not None else None
-        g_rot = torch.empty((P, 4), **f32) if rotations is not None else None
+        g_scales = out("scales", (P, 3)) if scales is not None else None
+        g_rot = out("rotations", (P, 4)) if rotations is not None else None
         g_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp is not None else None
         scratch = st.get_scratch(P)
         if not saved.pending.done:  # a forward that did not wait for its count: it has arrived by now
@@ -349,6 +360,28 @@ class _RasterizeGaussians(torch.autograd.Function):
                 check(L.rtg_splat_backward_finish(*args), "rtg_splat_backward_finish")
         # same order as the forward's arguments (reference __init__.py:269-279)
         return g_means, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov, None, None
+
+
+# Optional destination of the dense gradients (see `grad_buffers`); None = allocate per call.
+_GRAD_BUFFERS = [None]
+
+
+class grad_buffers:
+    """Context manager: while active, the rasterizer backward writes dL/d{means3D, shs, opacities, scales, rotations} into
+    the given tensors (dict by those names; e.g. `parallel.FlatGrads(P, dev).views`) instead of allocating new ones, so a
+    following all-reduce over the flat buffer needs no packing copy. The tensors returned to autograd alias them."""
+
+    def __init__(self, buffers):
+        self.buffers, self.prev = buffers, None
+
+    def __enter__(self):
+        self.prev = _GRAD_BUFFERS[0]
+        _GRAD_BUFFERS[0] = self.buffers
+        return self
+
+    def __exit__(self, *exc):
+        _GRAD_BUFFERS[0] = self.prev
+        return False
 
 
 # Optional exchange step of the backward: a callable that receives the (P, 16) fp32 gradient-record tensor after the

@@ -17,6 +17,34 @@ from ._lib import check
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 
 
+class _NormalMap(torch.autograd.Function):
+    """out (3,H,W) = normal[depth_index] where depth_index > -1, zeros elsewhere; backward scatter-adds the pixel
+    gradients onto the rows of `normal` (what autograd does for the reference's `normal[index]` expression, so that the
+    cosine normal loss of mapper.py:433-446 reaches the rotations)."""
+
+    @staticmethod
+    def forward(ctx, normal, depth_index):
+        if not normal.is_cuda or normal.dtype != torch.float32:
+            raise TypeError("gaussian_data['normal'] must be a CUDA float32 tensor")
+        H, W = depth_index.shape[-2:]
+        out = torch.empty((3, H, W), dtype=torch.float32, device=normal.device)
+        check(_lib.lib().rtg_normal_map(C.c_void_p(normal.detach().contiguous().data_ptr()), C.c_void_p(depth_index.contiguous().data_ptr()),
+                                        H, W, C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(normal.device).cuda_stream)),
+              "rtg_normal_map")
+        ctx.save_for_backward(depth_index)
+        ctx.n_rows = normal.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (depth_index,) = ctx.saved_tensors
+        idx = depth_index.reshape(-1).long()
+        valid = idx > -1
+        g = torch.zeros((ctx.n_rows, 3), dtype=grad_out.dtype, device=grad_out.device)
+        g.index_add_(0, idx[valid], grad_out.reshape(3, -1).t()[valid])
+        return g, None
+
+
 class Renderer:
     def __init__(self, args):
         self.raster_settings = None
@@ -73,15 +101,9 @@ class Renderer:
         )
         rendered_image, rendered_depth, color_index_map, depth_index_map, color_hit_weight, depth_hit_weight, T_map = res[:7]
 
-        # normal[depth_index_map] where the index is > -1, zeros elsewhere (render.py:130-133): one gather kernel
-        render_normal = torch.empty_like(rendered_image)
-        nrm = normal.detach()
-        if not nrm.is_cuda or nrm.dtype != torch.float32:
-            raise TypeError("gaussian_data['normal'] must be a CUDA float32 tensor")
-        H, W = rendered_image.shape[1:]
-        check(_lib.lib().rtg_normal_map(C.c_void_p(nrm.contiguous().data_ptr()), C.c_void_p(depth_index_map.data_ptr()), H, W,
-                                        C.c_void_p(render_normal.data_ptr()),
-                                        C.c_void_p(torch.cuda.current_stream(rendered_image.device).cuda_stream)), "rtg_normal_map")
+        # normal[depth_index_map] where the index is > -1, zeros elsewhere (render.py:130-133): one gather kernel,
+        # differentiable w.r.t. the per-Gaussian normals like the reference's indexing expression
+        render_normal = _NormalMap.apply(normal, depth_index_map)
 
         return {
             "render": rendered_image,

@@ -133,6 +133,16 @@ def test_renderer_api(cuda_device):
     ref = torch.zeros_like(out["render"])
     ref[:, idx > -1] = t["normal"][idx[idx > -1].long()].permute(1, 0)  # the reference's own expression (render.py:130-133)
     assert torch.equal(ref, out["normal"])
+    # the normal map is differentiable w.r.t. the per-Gaussian normals, as the reference's indexing expression is (the
+    # cosine normal loss of mapper.py:433-446 back-propagates through it)
+    na = t["normal"].clone().requires_grad_(True)
+    nb = t["normal"].clone().requires_grad_(True)
+    wts = torch.rand_like(out["render"])
+    (Renderer(args).render(vc, dict(data, normal=na))["normal"] * wts).sum().backward()
+    refn = torch.zeros_like(out["render"])
+    refn[:, idx > -1] = nb[idx[idx > -1].long()].permute(1, 0)
+    (refn * wts).sum().backward()
+    assert float((na.grad - nb.grad).abs().max()) <= 1e-5 * float(nb.grad.abs().max()) and float(nb.grad.abs().max()) > 0
 
 
 @pytest.mark.parametrize("use_mask", [False, True])

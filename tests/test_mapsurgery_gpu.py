@@ -17,10 +17,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _ref_simple_knn():
-    so = glob.glob(os.path.join(helpers.ROOT, "oracle", "_ref", "simple_knn", "_C*.so"))
+    so = glob.glob(os.path.join(helpers.ROOT, "oracle", "_ref", "simple_knn", "_C_simple_knn*.so"))
     if not so:
         return None
-    spec = importlib.util.spec_from_file_location("_C", so[0])
+    spec = importlib.util.spec_from_file_location("_C_simple_knn", so[0])
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
