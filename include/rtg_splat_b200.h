@@ -55,7 +55,9 @@ typedef struct RtgSplatView {
 } RtgSplatView;
 
 /* Device counters written by rtg_splat_forward (int32 each). */
-enum { RTG_CNT_NUM_RENDERED = 0, RTG_CNT_NUM_TILES = 1, RTG_CNT_OVERFLOW = 2, RTG_CNT_MAX_TILE_LEN = 3, RTG_CNT_WORDS = 8 };
+enum { RTG_CNT_NUM_RENDERED = 0, RTG_CNT_NUM_TILES = 1, RTG_CNT_OVERFLOW = 2, RTG_CNT_MAX_TILE_LEN = 3,
+       RTG_CNT_ENTRIES_NEEDED = 4, /* instances with every tile's bucket padded to 4 entries: what R_cap must hold */
+       RTG_CNT_WORDS = 8 };
 
 /* Sizes of the three state buffers kept between forward and backward. Replaces the
  * geomBuffer / imgBuffer / binningBuffer resize callbacks (RAST/rasterize_points.cu:27-35,

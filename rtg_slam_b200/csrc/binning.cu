@@ -17,20 +17,22 @@ namespace rtg {
 __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long long R_cap, int *__restrict__ counters,
                                                          int *__restrict__ counters_host) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry, s_max, s_nact;
+    __shared__ uint32_t s_carry, s_max, s_nact, s_sum;
     __shared__ uint32_t s_cls[66];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_max = 0; s_nact = 0; }
+    if (tid == 0) { s_carry = 0; s_max = 0; s_nact = 0; s_sum = 0; }
     if (tid < 66) s_cls[tid] = 0;
     __syncthreads();
-    uint32_t local_max = 0, local_act = 0;
+    uint32_t local_max = 0, local_act = 0, local_sum = 0;
     // (1) exclusive scan of the histogram -> tile offsets; (2) histogram of work classes for the launch order
     for (int base = 0; base < T; base += 1024) {
         const int i = base + tid;
         const uint32_t c = (i < T) ? b.tile_count[(size_t)i * RTG_CNT_STRIDE] : 0u;
+        const uint32_t cpad = (c + (RTG_LIST_ALIGN - 1)) & ~(uint32_t)(RTG_LIST_ALIGN - 1);  // bucket capacity
         local_max = max(local_max, c);
         local_act += (c > 0);
-        uint32_t v = c;
+        local_sum += c;
+        uint32_t v = cpad;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long
         __syncthreads();
         const uint32_t incl = v + (wid > 0 ? s_warp[wid - 1] : 0u) + s_carry;
         if (i < T) {
-            b.tile_offset[i] = incl - c;
+            b.tile_offset[i] = incl - cpad;
             // class 0 = longest lists (>= 4032 entries) ... class 63 = 1..63 entries, class 64 = empty tiles
             const int cls = (c == 0) ? 64 : 63 - (int)min(63u, c >> 6);
             atomicAdd(&s_cls[cls], 1u);
@@ -63,8 +65,9 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long
     for (int o = 16; o > 0; o >>= 1) {
         local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
         local_act += __shfl_xor_sync(0xffffffffu, local_act, o);
+        local_sum += __shfl_xor_sync(0xffffffffu, local_sum, o);
     }
-    if (lane == 0) { atomicMax(&s_max, local_max); atomicAdd(&s_nact, local_act); }
+    if (lane == 0) { atomicMax(&s_max, local_max); atomicAdd(&s_nact, local_act); atomicAdd(&s_sum, local_sum); }
     __syncthreads();
     // Launch order of the tiles: longest lists first (the block scheduler hands out CTAs in index order, so this
     // is longest-processing-time-first scheduling), empty tiles last. Order inside a class is irrelevant.
@@ -79,12 +82,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinState b, int T, long
         b.active[atomicAdd(&s_cls[cls], 1u)] = (uint32_t)i;
     }
     if (tid == 0) {
-        const uint32_t R = s_carry;
-        b.tile_offset[T] = R;
-        const int ov = ((long long)R > R_cap) ? 1 : 0;
-        counters[0] = (int)R; counters[1] = (int)s_nact; counters[2] = ov; counters[3] = (int)s_max;
+        const uint32_t Rpad = s_carry, R = s_sum;  // buffer entries needed (padded buckets) / instances
+        b.tile_offset[T] = Rpad;
+        const int ov = ((long long)Rpad > R_cap) ? 1 : 0;
+        counters[0] = (int)R; counters[1] = (int)s_nact; counters[2] = ov; counters[3] = (int)s_max; counters[4] = (int)Rpad;
         if (counters_host) {
             counters_host[0] = (int)R; counters_host[1] = (int)s_nact; counters_host[2] = ov; counters_host[3] = (int)s_max;
+            counters_host[4] = (int)Rpad;
         }
     }
 }
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
             if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, ga.w, gb.w, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
             const uint32_t slot = atomicAdd(b.tile_fill + (size_t)t * RTG_CNT_STRIDE, 1u);
             const uint32_t begin = b.tile_offset[t];
-            if (slot < b.tile_offset[t + 1] - begin)  // never write outside the bucket
+            if (slot < b.tile_count[(size_t)t * RTG_CNT_STRIDE])  // never write outside the bucket
                 b.keys[begin + slot] = ((uint64_t)s_depth[w][o] << 32) | (uint32_t)(base + o);
         }
     }
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(BinState b, con
     for (int ai = blockIdx.x; ai < nact; ai += gridDim.x) {
         const uint32_t tile = b.active[ai];
         const uint32_t start = b.tile_offset[tile];
-        const int n = (int)(b.tile_offset[tile + 1] - start);
+        const int n = (int)b.tile_count[(size_t)tile * RTG_CNT_STRIDE];
         uint64_t *gk = b.keys + start;
         uint32_t *out = b.point_list + start;
         if (n <= SORT_SMEM_KEYS) {

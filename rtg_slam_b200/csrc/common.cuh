@@ -43,7 +43,9 @@ struct BinState {
     uint32_t *tile_fill;    // [T*RTG_CNT_STRIDE] scatter cursors
     uint32_t *tile_touched; // [T]   1 if a Gaussian's rectangle covered the tile but the exact test culled it
     uint32_t *vis_count;    // [1]   number of entries of GeomState::vis_list
-    uint32_t *tile_offset;  // [T+1] exclusive scan of tile_count
+    uint32_t *tile_offset;  // [T+1] start of every tile's bucket: exclusive scan of the counts rounded up to RTG_LIST_ALIGN entries
+                            //       (16-byte aligned list starts: the lists are staged with TMA bulk copies). The number of
+                            //       entries of tile t is tile_count[t * RTG_CNT_STRIDE], NOT the offset difference.
     uint32_t *active;       // [T]   launch order of the tiles: longest list first, empty tiles last
     uint64_t *keys;         // [R_cap] (depth bits << 32 | gaussian id), bucketed by tile
     uint32_t *point_list;   // [R_cap] gaussian ids, per tile front-to-back
@@ -65,6 +67,8 @@ static inline T *carve(char *&p, size_t n) {
 // Words per tile in the tile histogram: counter of tile t is element t * RTG_CNT_STRIDE. L2 atomics on the same 32-byte
 // sector serialise, so neighbouring tiles do not share one (measured in round 1 on the then separate scatter cursors:
 // 0.077 -> 0.060 ms; splitting a tile's counter further into sub-buckets gained nothing).
+#define RTG_LIST_ALIGN 4    // tile buckets start at multiples of 4 entries (16 bytes)
+#define RTG_LIST_SLACK 260  // entries readable past the end of point_list
 #ifndef RTG_CNT_STRIDE
 #define RTG_CNT_STRIDE 8
 #endif
@@ -92,7 +96,7 @@ static inline BinState bin_from(void *ws, size_t T, size_t R_cap, size_t *bytes 
     b.tile_offset = carve<uint32_t>(p, T + 1);
     b.active = carve<uint32_t>(p, T);
     b.keys = carve<uint64_t>(p, R_cap);
-    b.point_list = carve<uint32_t>(p, R_cap);
+    b.point_list = carve<uint32_t>(p, R_cap + RTG_LIST_SLACK);  // a bulk copy of the last list may read up to one batch past it
     if (bytes) *bytes = (size_t)(p - reinterpret_cast<char *>(ws));
     return b;
 }
@@ -275,6 +279,29 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) of a contiguous global range into shared memory, completion on an
+// mbarrier. Source address, shared destination and byte count must be multiples of 16.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // explicit shared-state-space accesses with a precomputed 32-bit base (keeps address arithmetic out of the loops)

@@ -87,6 +87,10 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
     __shared__ float4 s_rec[2 * BATCH * 3];  // one 48-byte record per staged entry: splat half 0, half 1, colour
     __shared__ int s_id[2 * BATCH];
     __shared__ uint32_t s_mask[2 * BATCH];
+    // the tile's id list arrives by TMA: one bulk copy (cp.async.bulk -> UBLKCP) per batch of 256 ids, issued by one thread
+    // two batches ahead, completion on an mbarrier per buffer
+    __shared__ __align__(16) int s_list[2 * BATCH];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
 
     const int tile = (int)b.active[blockIdx.x];  // longest lists first
     int px, py;
@@ -97,8 +101,8 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
     const bool overflow = counters[2] != 0;
-    const uint32_t start = b.tile_offset[tile];
-    const int n = overflow ? 0 : (int)(b.tile_offset[tile + 1] - start);
+    const uint32_t start = b.tile_offset[tile];  // multiple of RTG_LIST_ALIGN entries: 16-byte aligned list
+    const int n = overflow ? 0 : (int)b.tile_count[(size_t)tile * RTG_CNT_STRIDE];
     if (n == 0) {
         if (inside) {
             // never-rendered tile: the wrapper's initial values (hit maps 0). A tile whose entries were all culled by
@@ -153,9 +157,31 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
         cp_async16(REC_RGB(slot), g.rgb_flags + id);
         sts32(a_id + slot * 4, (uint32_t)id);
     };
-    if ((int)threadIdx.x < n) stage(0, (int)b.point_list[start + threadIdx.x]);
+    const uint32_t a_list = smem_addr(s_list), a_mbar = smem_addr(s_mbar);
+    const int n_pad = (n + (RTG_LIST_ALIGN - 1)) & ~(RTG_LIST_ALIGN - 1);
+    // ids of batch k -> buffer k & 1 (its mbarrier completes for the (k >> 1)-th time); thread 0 only
+    auto issue_ids = [&](const int k) {
+        const int ents = min(BATCH, n_pad - k * BATCH);
+        if (ents > 0) {
+            mbar_expect_tx(a_mbar + (k & 1) * 8, (uint32_t)ents * 4u);
+            bulk_g2s(a_list + (uint32_t)((k & 1) * BATCH) * 4u, b.point_list + start + (size_t)k * BATCH, (uint32_t)ents * 4u,
+                     a_mbar + (k & 1) * 8);
+        }
+    };
+    auto wait_ids = [&](const int k) { mbar_wait(a_mbar + (k & 1) * 8, (uint32_t)((k >> 1) & 1)); };
+    if (threadIdx.x == 0) {
+        mbar_init(a_mbar, 1);
+        mbar_init(a_mbar + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { issue_ids(0); issue_ids(1); }
+    wait_ids(0);
+    if ((int)threadIdx.x < n) stage(0, (int)lds32(a_list + threadIdx.x * 4));
     cp_async_commit();
-    int id_next = (BATCH + (int)threadIdx.x < n) ? (int)b.point_list[start + BATCH + threadIdx.x] : -1;  // ids one batch ahead
+    __syncthreads();                                          // buffer 0 has been read by everybody
+    if (threadIdx.x == 0) issue_ids(2);
+    int consumed = 1;                                         // id batches < consumed have been read
     for (int i = 0; i < rounds; i++) {
         cp_async_wait_all();                                   // this thread's copies of batch i have landed
         if (__syncthreads_count(done) == BATCH) break;          // everybody's have; and batch i-1 is fully consumed
@@ -164,10 +190,15 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
             const float4 s0 = lds128(REC_S0(boff + threadIdx.x)), s1 = lds128(REC_S1(boff + threadIdx.x));
             sts32(a_mask + (boff + threadIdx.x) * 4, patch_mask(s0, s1, tx0, ty0));
         }
-        if (id_next >= 0) stage(i + 1, id_next);                // overlaps with the compositing of batch i
+        if ((i + 1) * BATCH < n) {                              // gathers of batch i + 1 overlap the compositing of batch i
+            wait_ids(i + 1);
+            consumed = i + 2;
+            if ((i + 1) * BATCH + (int)threadIdx.x < n)
+                stage(i + 1, (int)lds32(a_list + (uint32_t)(((i + 1) & 1) * BATCH + threadIdx.x) * 4));
+        }
         cp_async_commit();
-        id_next = ((i + 2) * BATCH + (int)threadIdx.x < n) ? (int)b.point_list[start + (i + 2) * BATCH + threadIdx.x] : -1;
         __syncthreads();
+        if (threadIdx.x == 0) issue_ids(i + 3);                // its buffer, (i + 1) & 1, has been read by everybody
         const int cnt = min(BATCH, n - i * BATCH);
         if (__all_sync(FULL, done)) continue;  // warp-uniform
         const int chunks = (cnt + 31) >> 5;
@@ -222,6 +253,10 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
         if (j_last >= 0) last_contributor = (uint32_t)(i * BATCH + j_last + 1);
         if (j_cmax >= 0) hit_color_id = (int)lds32(a_id + (boff + (uint32_t)j_cmax) * 4);
     }
+
+    // bulk copies that were issued for batches this CTA no longer needs must land before its shared memory is released
+    for (int k = consumed; k <= consumed + 1; k++)
+        if (k * BATCH < n_pad) wait_ids(k);
 
     if (inside) {
         const float bg0 = __ldg(vp.bg), bg1 = __ldg(vp.bg + 1), bg2 = __ldg(vp.bg + 2);
@@ -420,6 +455,10 @@ __global__ void BWD_BOUNDS render_bwd_kernel(const ViewParams vp, const GeomStat
     __shared__ int s_id[BATCH];
     __shared__ uint32_t s_mask[BATCH];
     __shared__ uint32_t s_max[4];
+    // the blended prefix of the tile's id list arrives by TMA, back to front: one bulk copy per round of 256 ids (plus
+    // up to 3 + 3 ids of alignment padding), issued by one thread two rounds ahead, completion on an mbarrier per buffer
+    __shared__ __align__(16) int s_list[2 * (BATCH + 8)];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
 #ifdef RTG_BWD_SMEM_REDUCE
     __shared__ float4 s_red[4][9 * 8];
     const uint32_t a_red = smem_addr(s_red[threadIdx.x >> 5]);
@@ -428,8 +467,8 @@ __global__ void BWD_BOUNDS render_bwd_kernel(const ViewParams vp, const GeomStat
     if (counters[2]) return;
     if ((int)blockIdx.x >= counters[1]) return;  // empty tiles sit at the end of the launch order
     const int tile = (int)b.active[blockIdx.x];
-    const uint32_t start = b.tile_offset[tile];
-    const int n = (int)(b.tile_offset[tile + 1] - start);
+    const uint32_t start = b.tile_offset[tile];  // multiple of RTG_LIST_ALIGN entries: 16-byte aligned list
+    const int n = (int)b.tile_count[(size_t)tile * RTG_CNT_STRIDE];
     if (n == 0) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int tx = tile % vp.tiles_x, ty = tile / vp.tiles_x;
@@ -472,12 +511,32 @@ __global__ void BWD_BOUNDS render_bwd_kernel(const ViewParams vp, const GeomStat
     const int my_slot = (lane & 1) ? -1 : reduce9_slot(lane);  // lanes 2k and 2k+1 hold the same total: one of them adds it
 
     const int rounds = ((int)m + BATCH - 1) / BATCH;
+    const uint32_t a_list = smem_addr(s_list), a_mbar = smem_addr(s_mbar);
+    // round k covers the list positions [lo, hi) = [max(0, m - (k+1)*256), m - k*256); the copy starts at lo rounded down to
+    // a 16-byte boundary and ends at hi rounded up to one (the extra ids are never read)
+    auto round_lo = [&](const int k) { return max(0, (int)m - (k + 1) * BATCH); };
+    auto issue_ids = [&](const int k) {  // thread 0 only
+        if (k < rounds) {
+            const int lo = round_lo(k) & ~(RTG_LIST_ALIGN - 1), hi = ((int)m - k * BATCH + (RTG_LIST_ALIGN - 1)) & ~(RTG_LIST_ALIGN - 1);
+            mbar_expect_tx(a_mbar + (k & 1) * 8, (uint32_t)(hi - lo) * 4u);
+            bulk_g2s(a_list + (uint32_t)((k & 1) * (BATCH + 8)) * 4u, b.point_list + start + lo, (uint32_t)(hi - lo) * 4u, a_mbar + (k & 1) * 8);
+        }
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(a_mbar, 1);
+        mbar_init(a_mbar + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { issue_ids(0); issue_ids(1); }
     for (int i = 0; i < rounds; i++) {
         __syncthreads();
+        mbar_wait(a_mbar + (i & 1) * 8, (uint32_t)((i >> 1) & 1));
+        const int lo_al = round_lo(i) & ~(RTG_LIST_ALIGN - 1);
         for (int q = threadIdx.x; q < BATCH; q += BWD_THREADS) {
             const int progress = i * BATCH + q;  // position from the back of the prefix
             if (progress < (int)m) {
-                const int id = (int)b.point_list[start + (m - 1 - progress)];
+                const int id = (int)lds32(a_list + (uint32_t)((i & 1) * (BATCH + 8) + ((int)m - 1 - progress - lo_al)) * 4u);
                 const float4 s0 = __ldg(g.splat + 2 * (size_t)id), s1 = __ldg(g.splat + 2 * (size_t)id + 1);
                 s_id[q] = id;
                 s_s0[q] = s0;
@@ -494,6 +553,7 @@ __global__ void BWD_BOUNDS render_bwd_kernel(const ViewParams vp, const GeomStat
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0) issue_ids(i + 2);  // buffer i & 1 has been read by everybody
         const int cnt = min(BATCH, (int)m - i * BATCH);
         const int chunks = (cnt + 31) >> 5;
         for (int c = 0; c < chunks; c++) {

@@ -323,10 +323,11 @@ class GaussianShard:
                                                  C.c_void_p(self.event.cuda_event), C.c_void_p(stream)), "rtg_splat_forward_render")
             self.event.synchronize()  # the scan kernel's counters (the compositing is still running)
             self.num_rendered, overflow = int(self.pinned[0]), int(self.pinned[2])
+            need = max(self.num_rendered, int(self.pinned[4]))  # with the tile buckets padded to 16-byte boundaries
             if overflow:
-                self.r_cap = int(self.num_rendered * 1.5) + 4096
+                self.r_cap = int(need * 1.5) + 4096
                 return False
-            self.r_cap = max(self.r_cap, int(self.num_rendered * 1.25) + 4096)
+            self.r_cap = max(self.r_cap, int(need * 1.25) + 4096)
             return True
 
         self._saved = (view, keep, M, means3D, shs, scales, rotations, outs, mask)

@@ -94,8 +94,9 @@ class _DeviceState:
         p.num_rendered, p.overflow = int(p.pinned[0]), bool(int(p.pinned[2]))
         self.last = tuple(int(x) for x in p.pinned[:4])
         p.done = True
+        # entries the buffer must hold: the instances with every tile's bucket padded to a 16-byte boundary (counters[4]);
         # 1.5x head room: the steady path does not wait for the count of the current frame
-        self.r_hint = max(self.r_hint, int(p.num_rendered * 1.5) + 4096)
+        self.r_hint = max(self.r_hint, int(max(p.num_rendered, int(p.pinned[4])) * 1.5) + 4096)
         self.free.append((p.pinned, p.event))  # the event has completed: the buffer may be reused
         p.pinned = p.event = None
         if p in self.pending:

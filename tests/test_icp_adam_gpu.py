@@ -233,3 +233,59 @@ def test_predict_pose_before_any_frame_raises_like_the_reference(cuda_device):
     trk.update_curr_status(torch.from_numpy(scene.raycast_room_depth(cam)).to(cuda_device), Kt)
     with pytest.raises(TypeError):
         trk.predict_pose({"K": Kt, "frame_id": 0})
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_mapping_loss_with_normal_and_ssim_terms(cuda_device, use_mask):
+    """rtg_slam_b200.loss.mapping_loss against the eager expressions of Mapping.loss_update (mapper.py:402-451) including
+    the cosine normal term and -- without a render mask, as in the reference -- the SSIM term of utils/loss_utils.py;
+    values, gradients, and the single read-back of the reported losses."""
+    import torch.nn.functional as F
+    from rtg_slam_b200.loss import mapping_loss, report_losses
+    dev = cuda_device
+    torch.manual_seed(5)
+    H, W = 70, 90
+    render = torch.rand(3, H, W, device=dev, requires_grad=True)
+    depth = (torch.rand(1, H, W, device=dev) * 3).requires_grad_(True)
+    normal = F.normalize(torch.randn(3, H, W, device=dev), dim=0).requires_grad_(True)
+    depth_index = torch.randint(-1, 50, (1, H, W), device=dev, dtype=torch.int32)
+    gt_color = torch.rand(H, W, 3, device=dev)
+    gt_depth = depth.detach().permute(1, 2, 0) + 0.05 * torch.randn(H, W, 1, device=dev)
+    gt_depth[torch.rand(H, W, 1, device=dev) < 0.1] = 0
+    gt_normal = F.normalize(torch.randn(H, W, 3, device=dev), dim=-1)
+    gt_normal[torch.rand(H, W, device=dev) < 0.15] = 0
+    mask = (torch.rand(H, W, device=dev) < 0.6) if use_mask else None
+    w = dict(color_weight=0.8, depth_weight=1.0, normal_weight=0.1, ssim_weight=0.2)
+    loss, parts = mapping_loss({"render": render, "depth": depth, "normal": normal, "depth_index_map": depth_index},
+                               {"color_map": gt_color, "depth_map": gt_depth, "normal_map": gt_normal}, render_mask=mask,
+                               depth_error_max=0.1, **w)
+    loss.backward()
+    got = [t.grad.clone() for t in (render, depth, normal)]
+    for t in (render, depth, normal):
+        t.grad = None
+    # the reference's expressions
+    image, d, n, di = render.permute(1, 2, 0), depth.permute(1, 2, 0), normal.permute(1, 2, 0), depth_index.permute(1, 2, 0)
+    ssim_loss = torch.zeros((), device=dev)
+    if mask is None:
+        rm = torch.ones(H, W, dtype=torch.bool, device=dev)
+        from rtg_slam_b200.loss import _ssim_term
+        ssim_loss = _ssim_term(image.permute(2, 0, 1), gt_color.permute(2, 0, 1))
+    else:
+        rm = mask.bool()
+    color_loss = torch.abs(image[rm] - gt_color[rm]).mean()
+    err = d - gt_depth
+    valid = (di != -1).squeeze() & (gt_depth > 0).squeeze() & (err < 0.1).squeeze() & rm
+    depth_loss = torch.abs(err[valid]).mean()
+    cos_dist = 1 - F.cosine_similarity(n, gt_normal, dim=-1)
+    vn = rm & (di != -1).squeeze() & (~(gt_normal == 0).all(dim=-1))
+    normal_loss = cos_dist[vn].mean()
+    ref = w["depth_weight"] * depth_loss + w["normal_weight"] * normal_loss + w["color_weight"] * color_loss + w["ssim_weight"] * ssim_loss
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) < 1e-5 * max(1.0, abs(float(ref.detach())))
+    for a, t in zip(got, (render, depth, normal)):
+        assert float((a - t.grad).abs().max()) < 1e-9 + 2e-5 * float(t.grad.abs().max())
+    rep = report_losses(parts, scale_loss=torch.tensor(0.25, device=dev))
+    assert set(rep) == {"total_loss", "depth_loss", "ssim_loss", "normal_loss", "color_loss", "scale_loss"}
+    assert abs(rep["normal_loss"] - float(normal_loss)) < 1e-5 and abs(rep["color_loss"] - float(color_loss)) < 1e-6
+    assert abs(rep["ssim_loss"] - float(ssim_loss)) < 1e-6 and rep["scale_loss"] == 0.25
+    assert int(parts[5]) == int(vn.sum())
