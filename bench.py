@@ -571,7 +571,38 @@ def gaussian_sharded(args, dev, world, rank, barrier, P=4_000_000, camera="repli
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms = float(tm.item()) / n
     ex = sh.exchange_bytes()
+    # where the step goes (rank 0, a few extra steps outside the timed region): library kernels by their own event
+    # profiler, the two exchanges by CUDA events around the collectives
+    from rtg_slam_b200 import _lib
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    coll_ms = {"all_gather": 0.0, "reduce_scatter": 0.0}
+    orig_ag, orig_rs = sh.exchange_records_forward, sh.coll.reduce_scatter_rows
+
+    def timed(name, fn):
+        def wrapped(*a, **k):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            r = fn(*a, **k)
+            a1.record()
+            torch.cuda.synchronize()
+            coll_ms[name] += a0.elapsed_time(a1)
+            return r
+        return wrapped
+    sh.exchange_records_forward = timed("all_gather", orig_ag)
+    sh.coll.reduce_scatter_rows = timed("reduce_scatter", orig_rs)
+    m = 3
+    for _ in range(m):
+        it()
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    prof = _lib.profile_read(reset=True)
+    sh.exchange_records_forward, sh.coll.reduce_scatter_rows = orig_ag, orig_rs
+    breakdown = {k: round(v[0] / m, 4) for k, v in prof.items() if v[1] > 0}
+    breakdown.update({k: round(v / m, 4) for k, v in coll_ms.items()})
+    barrier()
     return {"frames_per_s": 1e3 / ms, "ms_per_step": ms, "gaussians": P, "scaling": "strong", "num_rendered_own_tiles": int(sh.num_rendered),
+            "breakdown_ms_rank0": breakdown, "longest_tile_list_rank0": int(sh.pinned[3]),
             "all_gather_bytes_received": ex["all_gather"], "reduce_scatter_bytes_received": ex["reduce_scatter"],
             "note": "BASELINE configs[4]: ONE frame per step for the whole job; each rank owns P/N Gaussians (parameters, Adam state) and "
                     "1/N of the tiles: forward preprocess of the owned Gaussians, ncclAllGather of the 84-byte records, binning + "

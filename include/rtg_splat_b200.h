@@ -137,7 +137,10 @@ int rtg_splat_backward_finish(const RtgSplatView *view, int32_t P, int32_t M, co
  *                                 `radii` (P entries) -- then all-gather those rows across ranks (their byte offsets inside
  *                                 the workspace: rtg_splat_geom_layout; splat 32 B, colour 16 B, surfel 32 B per Gaussian);
  *   rtg_splat_forward_render      tile histogram of ALL P records over the tiles of `tile_mask` (this rank's tiles), scan,
- *                                 scatter, per-tile sort, compositing: outputs as rtg_splat_forward, valid on those tiles;
+ *                                 scatter, per-tile sort, compositing: outputs as rtg_splat_forward, valid on those tiles.
+ *                                 [tile_row_begin, tile_row_end): tile rows outside which tile_mask is all zero (a rank that
+ *                                 owns a band of rows passes it so that the binning passes clip every rectangle to the band
+ *                                 before expanding it: per-rank work / N instead of constant); 0, 0 = no clipping;
  *   rtg_splat_backward_render_shard   compositing backward over this rank's tiles into `grad2d_scratch` (P records, zero on
  *                                 entry) + zero-fill of the owned gradient rows -- then reduce-scatter the records so that
  *                                 the owner of [p_begin, p_end) holds their sums;
@@ -153,7 +156,8 @@ int rtg_splat_forward_preprocess(const RtgSplatView *view, int32_t P, int32_t p_
 int rtg_splat_forward_render(const RtgSplatView *view, int32_t P, const int32_t *tile_mask, void *geom_ws, void *img_ws, void *bin_ws,
                              int64_t R_cap, float *out_color, float *out_depth, int32_t *out_hit_color, int32_t *out_hit_depth,
                              float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, const int32_t *radii,
-                             int32_t *counters, int32_t *counters_host, void *scan_done_event, void *stream);
+                             int32_t *counters, int32_t *counters_host, void *scan_done_event, int32_t tile_row_begin,
+                             int32_t tile_row_end, void *stream);
 int rtg_splat_backward_render_shard(int32_t p_begin, int32_t p_end, const RtgSplatView *view, int32_t P, int32_t M,
                                     const float *means3D, const float *shs, const float *colors_precomp, const float *scales,
                                     const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom_ws,

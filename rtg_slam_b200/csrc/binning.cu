@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
         s0 = g.splat[2 * (size_t)idx];
         s1 = g.splat[2 * (size_t)idx + 1];
         tile_rect(make_float2(s0.x, s0.y), r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
+        y0 = max(y0, vp.row_begin); y1 = max(y0, min(y1, vp.row_end));  // rows outside the rank's band hold no tile of its mask
     }
     const int npairs = (x1 - x0) * (y1 - y0);
     const int incl = warp_incl_scan(npairs, lane);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ViewParams vp, int P
             if (rect_below_cutoff(ga.x, ga.y, gb.x, gb.y, gb.z, ga.z, ga.w, gb.w, fx0, fx0 + (RTG_TILE - 1), fy0, fy0 + (RTG_TILE - 1))) continue;
             const uint32_t slot = atomicAdd(b.tile_fill + (size_t)t * RTG_CNT_STRIDE, 1u);
             const uint32_t begin = b.tile_offset[t];
-            if (slot < b.tile_count[(size_t)t * RTG_CNT_STRIDE])  // never write outside the bucket
+            if (begin + slot < b.tile_offset[t + 1])  // never write outside the (padded) bucket
                 b.keys[begin + slot] = ((uint64_t)s_depth[w][o] << 32) | (uint32_t)(base + o);
         }
     }
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) tile_histogram_kernel(const ViewParams vp
         s0 = g.splat[2 * (size_t)idx];
         s1 = g.splat[2 * (size_t)idx + 1];
         tile_rect(make_float2(s0.x, s0.y), r, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
+        y0 = max(y0, vp.row_begin); y1 = max(y0, min(y1, vp.row_end));  // rows outside the rank's band hold no tile of its mask
     }
     const int npairs = (x1 - x0) * (y1 - y0);
     const int incl = warp_incl_scan(npairs, lane);

@@ -72,7 +72,12 @@ static const char *kKernelNames[K_COUNT] = {"preprocess_fwd", "tile_scan", "scat
 static thread_local std::string g_err;
 
 // one non-blocking side stream (+ fork / join events) per device, created on first use
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+    std::mutex use;  // held across record(fork) .. wait(join): two host threads running a backward on the same device must not
+                     // re-record the shared events between another thread's record and wait
+};
 static SideStream *side_stream() {
     static std::mutex mu;
     static SideStream table[64];
@@ -125,6 +130,8 @@ static rtg::ViewParams make_view(const RtgSplatView *v) {
     p.proj = v->projmatrix;
     p.campos = v->campos;
     p.bg = v->bg;
+    p.row_begin = 0;
+    p.row_end = p.tiles_y;
     return p;
 }
 
@@ -283,7 +290,8 @@ int rtg_splat_forward_preprocess(const RtgSplatView *view, int32_t P, int32_t p_
 int rtg_splat_forward_render(const RtgSplatView *view, int32_t P, const int32_t *tile_mask, void *geom_ws, void *img_ws, void *bin_ws,
                              int64_t R_cap, float *out_color, float *out_depth, int32_t *out_hit_color, int32_t *out_hit_depth,
                              float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, const int32_t *radii,
-                             int32_t *counters, int32_t *counters_host, void *scan_done_event, void *stream) {
+                             int32_t *counters, int32_t *counters_host, void *scan_done_event, int32_t tile_row_begin,
+                             int32_t tile_row_end, void *stream) {
     int rc = validate_view(view, "rtg_splat_forward_render");
     if (rc) return rc;
     if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward_render: P < 0");
@@ -291,7 +299,11 @@ int rtg_splat_forward_render(const RtgSplatView *view, int32_t P, const int32_t 
         !counters || !geom_ws || !img_ws || !bin_ws || !tile_mask || (P > 0 && !radii))
         return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_splat_forward_render: NULL output / workspace / tile_mask / radii pointer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const rtg::ViewParams vp = make_view(view);
+    rtg::ViewParams vp = make_view(view);
+    if (tile_row_end > tile_row_begin) {  // the rows that hold this rank's tiles: rectangles are clipped to them before expansion
+        vp.row_begin = tile_row_begin < 0 ? 0 : tile_row_begin;
+        vp.row_end = tile_row_end > vp.tiles_y ? vp.tiles_y : tile_row_end;
+    }
     const int T = vp.tiles_x * vp.tiles_y;
     rtg::GeomState g = rtg::geom_from(geom_ws, (size_t)P);
     rtg::ImgState img = rtg::img_from(img_ws, (size_t)vp.H * vp.W);
@@ -341,6 +353,8 @@ static int splat_backward_impl(int phase, int32_t p_begin, int32_t p_end, const 
     // the compute-bound render backward runs, and joins before the call's work on `s` ends
     if (phase != 2) {
         SideStream *ss = side_stream();
+        std::unique_lock<std::mutex> side_lock;
+        if (ss) side_lock = std::unique_lock<std::mutex>(ss->use);
         cudaError_t e = ss ? cudaEventRecord(ss->fork, s) : cudaErrorUnknown;
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
         const bool forked = (e == cudaSuccess);

@@ -25,6 +25,7 @@ struct ViewParams {
     float scale_modifier, color_sigma, opaque_thr, depth_thr, normal_thr, T_thr;
     int sh_degree, prefiltered;
     const float *view, *proj, *campos, *bg;
+    int row_begin, row_end;  // tile rows the binning passes expand (a rank's band in the Gaussian-sharded forward); else all
 };
 
 // Per-Gaussian state written by the forward preprocess (16-byte records so that every gather in the render

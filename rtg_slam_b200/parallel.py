@@ -103,13 +103,25 @@ class TileShard:
     TILE = 16
 
     def __init__(self, H: int, W: int, world_size: int | None = None, r: int | None = None, base_mask: torch.Tensor | None = None,
-                 weights: torch.Tensor | None = None, device="cpu"):
+                 weights: torch.Tensor | None = None, device="cpu", bands: bool = False):
         self.H, self.W = H, W
         self.world = world() if world_size is None else world_size
         self.rank = rank() if r is None else r
         th, tw = (H + self.TILE - 1) // self.TILE, (W + self.TILE - 1) // self.TILE
         self.tile_grid = (th, tw)
-        self.owner = self._owners(th * tw, self.world, weights).view(th, tw)
+        if bands:
+            # contiguous bands of tile rows with (nearly) equal total weight: row r goes to the rank whose share of the
+            # cumulative weight its midpoint falls into
+            row_w = torch.ones(th, dtype=torch.float64) if weights is None else \
+                weights.detach().to("cpu", torch.float64).reshape(th, tw).sum(1).clamp_min(1e-12)
+            mid = torch.cumsum(row_w, 0) - 0.5 * row_w
+            own_row = torch.clamp((mid / row_w.sum() * self.world).floor().long(), 0, self.world - 1)
+            self.owner = own_row[:, None].expand(th, tw).contiguous()
+            mine_rows = torch.nonzero(own_row == self.rank).flatten()
+            self.rows = (int(mine_rows[0]), int(mine_rows[-1]) + 1) if mine_rows.numel() else (0, 0)
+        else:
+            self.owner = self._owners(th * tw, self.world, weights).view(th, tw)
+            self.rows = (0, th)
         mine = self.owner == self.rank
         if base_mask is not None:
             mine = mine & (base_mask.to("cpu") != 0)
@@ -247,7 +259,10 @@ class GaussianShard:
         self.rank = rank() if r is None else r
         self.device = torch.device(device)
         self.p_begin, self.p_end = shard_range(P, self.world, self.rank)
-        self.tiles = TileShard(H, W, self.world, self.rank, weights=tile_weights, device=self.device)
+        # tiles: a band of tile rows per rank (contiguous, so that the binning passes can clip every Gaussian's rectangle
+        # to the band before expanding it); `tile_weights` (per tile, e.g. the previous frame's list lengths) balances the bands
+        self.tiles = TileShard(H, W, self.world, self.rank, weights=tile_weights, device=self.device, bands=True)
+        self.row_begin, self.row_end = self.tiles.rows
         self.coll = collectives if collectives is not None else _Collectives(self.world, self.rank)
         self.r_cap = 1 << 16
         self._lib = _lib
@@ -320,7 +335,8 @@ class GaussianShard:
             visible-list counter lives in the binning workspace, which moves)."""
             lib.check(L.rtg_splat_forward_render(C.byref(view), P, p(mask), p(self.geom), p(self.img), p(self.bin), self.r_cap,
                                                  *[p(o) for o in outs], p(self.radii), p(self.counters), C.c_void_p(self.pinned.data_ptr()),
-                                                 C.c_void_p(self.event.cuda_event), C.c_void_p(stream)), "rtg_splat_forward_render")
+                                                 C.c_void_p(self.event.cuda_event), self.row_begin, self.row_end, C.c_void_p(stream)),
+                      "rtg_splat_forward_render")
             self.event.synchronize()  # the scan kernel's counters (the compositing is still running)
             self.num_rendered, overflow = int(self.pinned[0]), int(self.pinned[2])
             need = max(self.num_rendered, int(self.pinned[4]))  # with the tile buckets padded to 16-byte boundaries
