@@ -11,7 +11,7 @@
  * (SURVEY.md section 4). This restatement is pinned against outputs of the
  * reference's own CUDA code (RAST built unmodified for sm_100 into
  * oracle/_ref/, run on a B200) stored under tests/golden/ -- see
- * tests/golden/README.md and tests/test_oracle_golden.py.
+ * tests/golden/README.md and tests/test_oracle_raster.py.
  *
  * Build twice from this one file: -DREAL=float (mirrors the reference's fp32
  * arithmetic incl. its accidental double-precision sub-expressions) and

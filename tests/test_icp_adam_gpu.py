@@ -74,7 +74,16 @@ def test_fill_model_depth(cuda_device):
     rd = torch.from_numpy(g["fill_render_depth"].copy()).to(cuda_device)[..., None].contiguous()
     trk.update_last_status(None, rd, torch.from_numpy(g["depth0"]).to(cuda_device)[..., None],
                            torch.from_numpy(g["fill_render_normal"]).to(cuda_device), torch.from_numpy(n0[-1]).to(cuda_device))
-    assert (rd[..., 0].cpu().numpy() != g["fill_out"]).mean() < 1e-3
+    got = rd[..., 0].cpu().numpy()
+    diff = got != g["fill_out"]
+    # the only pixels that may differ from the reference's result are those whose fill decision sits on one of its two
+    # thresholds to fp32 rounding (|render - frame depth| vs 0.01 m; 1 - cos(normals) vs 0.01, the golden's frame normals
+    # being the reference's own, the test's the oracle's: equal to 1e-5): name them, and require all others to be exact
+    rdep, fdep, rn, fn = g["fill_render_depth"], g["depth0"], g["fill_render_normal"], n0[-1]
+    cos = (rn * fn).sum(-1) / (np.maximum(np.linalg.norm(rn, axis=-1), 1e-8) * np.maximum(np.linalg.norm(fn, axis=-1), 1e-8))
+    borderline = (np.abs(np.abs(rdep - fdep) - 0.01) < 1e-6) | (np.abs((1 - cos) - 0.01) < 2e-4)
+    assert not np.any(diff & ~borderline), int((diff & ~borderline).sum())
+    assert diff.mean() < 1e-3
     assert trk.last_model_depth is rd
 
 
