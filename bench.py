@@ -807,6 +807,14 @@ def icp_section(dev, cam):
     b.record()
     torch.cuda.synchronize()
     out["device_ms_per_predict_pose"] = a.elapsed_time(b) / n
+    from rtg_slam_b200 import _lib
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    for _ in range(20):
+        trk.predict_pose(frame)
+    _lib.profile_enable(False)
+    prof = _lib.profile_read(reset=True)
+    out["kernel_ms"] = {"pyramid (model depth)": prof["icp_build_level"][0] / 20, "solve + loss (one cooperative kernel)": prof["icp_iter"][0] / 20}
     # roofline: 48 B per pixel and iteration, 5 iterations on each of the three levels
     bytes_solve = 48 * 5 * (H * W + (H // 2) * (W // 2) + (H // 4) * (W // 4))
     peak = 6650.0

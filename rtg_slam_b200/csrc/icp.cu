@@ -138,66 +138,93 @@ __device__ __forceinline__ float warp_transpose_reduce32(float v[32], const int 
     return v[0];  // lane L holds value index bitrev-free: (b4<<4|b3<<3|b2<<2|b1<<1|b0) == L
 }
 
-// exp_se3 (SLAM/icp.py:271-310) and pose <- exp(xi) @ pose (forward_update_pose :259-268)
-__device__ void se3_update(const double xi[6], float *pose) {
+// exp_se3 (SLAM/icp.py:271-310) and pose <- exp(xi) @ pose (forward_update_pose :259-268). Every loop has a
+// compile-time trip count and is unrolled: the small matrices live in registers (the serial tail of every iteration
+// runs on one thread; with dynamically indexed local arrays it cost more than the per-pixel pass of the coarse levels).
+__device__ __forceinline__ void se3_update(const double xi[6], float *pose) {
     const double w0 = xi[0], w1 = xi[1], w2 = xi[2];
     const double Wh[3][3] = {{0.0, -w2, w1}, {w2, 0.0, -w0}, {-w1, w0, 0.0}};
     double W2[3][3];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) W2[i][j] = Wh[i][0] * Wh[0][j] + Wh[i][1] * Wh[1][j] + Wh[i][2] * Wh[2][j];
     const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
     double E[3][3], J[3][3];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) { E[i][j] = (i == j); J[i][j] = (i == j); }
     if (!(theta <= 1e-8)) {
-        const double th2 = theta * theta, th3 = th2 * theta, s = sin(theta), c = cos(theta);
-        const double k1 = (1.0 - c) / th2, k2 = (theta - s) / th3;
+        const double th2 = theta * theta, th3 = th2 * theta, sn = sin(theta), cs = cos(theta);
+        const double k1 = (1.0 - cs) / th2, k2 = (theta - sn) / th3;
+#pragma unroll
         for (int i = 0; i < 3; i++)
+#pragma unroll
             for (int j = 0; j < 3; j++) {
-                E[i][j] += Wh[i][j] * s / theta + W2[i][j] * (1.0 - c) / th2;
+                E[i][j] += Wh[i][j] * sn / theta + W2[i][j] * (1.0 - cs) / th2;
                 J[i][j] += k1 * Wh[i][j] + k2 * W2[i][j];
             }
     }
-    double Tm[4][4] = {{0}};
+    double Tm[3][4];
+#pragma unroll
     for (int i = 0; i < 3; i++) {
+#pragma unroll
         for (int j = 0; j < 3; j++) Tm[i][j] = E[i][j];
         Tm[i][3] = J[i][0] * xi[3] + J[i][1] * xi[4] + J[i][2] * xi[5];
     }
-    Tm[3][3] = 1.0;
-    double P[4][4], O[4][4];
+    double P[4][4];
+#pragma unroll
     for (int i = 0; i < 4; i++)
+#pragma unroll
         for (int j = 0; j < 4; j++) P[i][j] = (double)pose[4 * i + j];
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) O[i][j] = Tm[i][0] * P[0][j] + Tm[i][1] * P[1][j] + Tm[i][2] * P[2][j] + Tm[i][3] * P[3][j];
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) pose[4 * i + j] = (float)O[i][j];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            pose[4 * i + j] = (float)(Tm[i][0] * P[0][j] + Tm[i][1] * P[1][j] + Tm[i][2] * P[2][j] + Tm[i][3] * P[3][j]);
+    // the last row of exp(xi) is (0, 0, 0, 1): the pose's last row is unchanged
 }
 
-// Solve (JtJ + trace*damping*I) xi = -Jtr by Gaussian elimination with partial pivoting (the reference
-// inverts the same matrix with torch.inverse on the CPU, SLAM/icp.py:248-257,313-333).
-__device__ bool solve6(double A[6][6], double bvec[6], double x[6]) {
-    for (int k = 0; k < 6; k++) {
-        int piv = k;
-        double best = fabs(A[k][k]);
-        for (int i = k + 1; i < 6; i++)
-            if (fabs(A[i][k]) > best) { best = fabs(A[i][k]); piv = i; }
-        if (best == 0.0) return false;
-        if (piv != k) {
-            for (int j = 0; j < 6; j++) { const double tmp = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = tmp; }
-            const double tb = bvec[k]; bvec[k] = bvec[piv]; bvec[piv] = tb;
-        }
-        for (int i = k + 1; i < 6; i++) {
-            const double f = A[i][k] / A[k][k];
-            for (int j = k; j < 6; j++) A[i][j] -= f * A[k][j];
-            bvec[i] -= f * bvec[k];
+// Solve (JtJ + trace*damping*I) xi = -Jtr (the reference inverts the same matrix with torch.inverse on the CPU,
+// SLAM/icp.py:248-257,313-333). The damped normal matrix is symmetric positive definite: Cholesky without pivoting, fully
+// unrolled (registers only), double precision. Returns false if a pivot is not positive (degenerate view: pose unchanged).
+__device__ __forceinline__ bool solve6(const double A[6][6], const double bvec[6], double x[6]) {
+    double Lm[6][6];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double d = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= Lm[j][k] * Lm[j][k];
+        ok = ok && (d > 0.0);
+        const double ljj = sqrt(fmax(d, 1e-300));
+        Lm[j][j] = ljj;
+        const double inv = 1.0 / ljj;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double v = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= Lm[i][k] * Lm[j][k];
+            Lm[i][j] = v * inv;
         }
     }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double v = bvec[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) v -= Lm[i][k] * y[k];
+        y[i] = v / Lm[i][i];
+    }
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
-        double sacc = bvec[i];
-        for (int j = i + 1; j < 6; j++) sacc -= A[i][j] * x[j];
-        x[i] = sacc / A[i][i];
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) v -= Lm[k][i] * x[k];
+        x[i] = v / Lm[i][i];
     }
-    return true;
+    return ok;
 }
 
 // One Gauss-Newton iteration (compute_residuals_jacobian + compute_jtj/jtr + GN_solver, SLAM/icp.py:52-130).
@@ -293,11 +320,14 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_iter_kernel(const float *__re
         __syncwarp();
         if (lane == 0) {
             double A[6][6], bvec[6], xi[6];
-            int k = 0;
+#pragma unroll
             for (int a = 0; a < 6; a++)
-                for (int c = a; c < 6; c++) { A[a][c] = s_tot[k]; A[c][a] = s_tot[k]; k++; }
+#pragma unroll
+                for (int c = a; c < 6; c++) { const double v = s_tot[a * 6 - a * (a - 1) / 2 + (c - a)]; A[a][c] = v; A[c][a] = v; }
             double trace = 0.0;
+#pragma unroll
             for (int a = 0; a < 6; a++) trace += A[a][a];
+#pragma unroll
             for (int a = 0; a < 6; a++) { A[a][a] += trace * (double)damping; bvec[a] = -s_tot[21 + a]; }
             if (solve6(A, bvec, xi)) se3_update(xi, pose);
             if (valid_ratio) *valid_ratio = (float)(s_tot[27] / (double)H / (double)W);
@@ -503,11 +533,14 @@ __global__ void __launch_bounds__(ICP_P_THREADS) icp_predict_kernel(const IcpPre
             icp_grid_total(partial, s_part, s_tot);
             if (threadIdx.x == 0) {
                 double A[6][6], bvec[6], xi[6];
-                int k = 0;
+#pragma unroll
                 for (int a = 0; a < 6; a++)
-                    for (int c = a; c < 6; c++) { A[a][c] = s_tot[k]; A[c][a] = s_tot[k]; k++; }
+#pragma unroll
+                    for (int c = a; c < 6; c++) { const double v = s_tot[a * 6 - a * (a - 1) / 2 + (c - a)]; A[a][c] = v; A[c][a] = v; }
                 double trace = 0.0;
+#pragma unroll
                 for (int a = 0; a < 6; a++) trace += A[a][a];
+#pragma unroll
                 for (int a = 0; a < 6; a++) { A[a][a] += trace * (double)prm.damping; bvec[a] = -s_tot[21 + a]; }
                 if (solve6(A, bvec, xi)) se3_update(xi, s_pose);
                 s_valid = (float)(s_tot[27] / (double)L.H / (double)L.W);
