@@ -209,6 +209,62 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
             const int e = (c << 5) + lane;
             const uint32_t mm = (e < cnt) ? lds32(a_mask + (boff + e) * 4) : 0u;
             uint32_t bits = __ballot_sync(FULL, (mm >> w) & 1u);
+            // everything after the alpha of a (pixel, entry) pair (forward.cu:772-838)
+            auto blend = [&](const int j, const uint32_t jb, const float4 s0, const float power, const float alpha) {
+                if (alpha >= opaque_lo) {  // at most a few entries per pixel (opaque_lo = +inf after the hit)
+                    // inside the band the decision is taken on the reference's own expression
+                    const float a_dec = (alpha < vp.opaque_thr * (1.0f + RTG_ALPHA_BAND)) ? fminf(0.99f, s0.w * expf(power)) : alpha;
+                    if (a_dec >= vp.opaque_thr) {
+                        const int id = (int)lds32(a_id + jb * 4);
+                        const float4 h0 = __ldg(g.hit + 2 * (size_t)id), h1 = __ldg(g.hit + 2 * (size_t)id + 1);
+                        depth_ = surfel_depth(h0, h1, ray, h1.z, vp.depth_thr, vp.normal_thr);
+                        hit_id = id;
+                        hit_dw = alpha * T;
+                        hit = true;
+                        opaque_lo = __int_as_float(0x7f800000);
+                    }
+                }
+                const float test_T = T * (1.f - alpha);
+                if (test_T < T_thr) {
+                    // no colour is added any more; the pixel keeps scanning until it has an opaque hit
+                    if (hit) { done = true; pfx = FAR; }
+                    else T = test_T;
+                } else {
+                    const float cw = alpha * T;
+                    const float4 col = lds128(REC_RGB(jb));
+                    C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
+                    if (cw > cw_max) { cw_max = cw; j_cmax = j; }
+                    j_last = j;
+                    end_T = test_T;
+                    T = test_T;
+                }
+            };
+#ifndef RTG_FWD_ILP1  // -DRTG_FWD_ILP1: one entry per iteration (0.279 ms instead of 0.265 ms on configs[1])
+            // two entries in flight per warp: their records, exponents and alphas are independent (only the blend is
+            // sequential in T), which halves the dependent latency chain of a warp's walk -- what bounds a heavy tile
+            while (bits) {
+                const int ja = (c << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const bool two = bits != 0u;  // warp-uniform
+                const int jc = two ? (c << 5) + __ffs(bits) - 1 : ja;
+                if (two) bits &= bits - 1;
+                const uint32_t jba = boff + (uint32_t)ja, jbc = boff + (uint32_t)jc;
+                const float4 s0a = lds128(REC_S0(jba)), s1a = lds128(REC_S1(jba));
+                const float4 s0c = lds128(REC_S0(jbc)), s1c = lds128(REC_S1(jbc));
+                const float pwa = pair_power(s1a.x, s1a.y, s1a.z, s0a.x - pfx, s0a.y - pfy);
+                const float pwc = pair_power(s1c.x, s1c.y, s1c.z, s0c.x - pfx, s0c.y - pfy);
+                float ala, aua, alc, auc;
+                bool banda, bandc;
+                bool oka = pair_alpha_fast(pwa, s1a.w, ala, aua, banda) && RTG_FWD_PRETEST(pwa, s0a.z);
+                bool okc = pair_alpha_fast(pwc, s1c.w, alc, auc, bandc) && RTG_FWD_PRETEST(pwc, s0c.z) && two;
+                if ((banda && oka) || (bandc && okc)) {  // a few pairs per frame
+                    if (banda && oka) oka = pair_alpha_exact(pwa, s0a.w, ala, aua);
+                    if (bandc && okc) okc = pair_alpha_exact(pwc, s0c.w, alc, auc);
+                }
+                if (oka) blend(ja, jba, s0a, pwa, ala);
+                if (okc && !done) blend(jc, jbc, s0c, pwc, alc);  // the pixel may have finished on the first entry
+            }
+#else
             while (bits) {
                 const int j = (c << 5) + __ffs(bits) - 1;
                 const uint32_t jb = boff + (uint32_t)j;
@@ -218,36 +274,9 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(const ViewParams vp, co
                 const float power = pair_power(s1.x, s1.y, s1.z, dx, dy);
                 // power > 0: skipped by the reference; finished pixel: power = -inf or NaN, never passes
                 float alpha, au;
-                if (RTG_FWD_PRETEST(power, s0.z) && pair_alpha(power, s1.w, s0.w, alpha, au)) {
-                    if (alpha >= opaque_lo) {  // at most a few entries per pixel (opaque_lo = +inf after the hit)
-                        // inside the band the decision is taken on the reference's own expression
-                        const float a_dec = (alpha < vp.opaque_thr * (1.0f + RTG_ALPHA_BAND)) ? fminf(0.99f, s0.w * expf(power)) : alpha;
-                        if (a_dec >= vp.opaque_thr) {
-                            const int id = (int)lds32(a_id + jb * 4);
-                            const float4 h0 = __ldg(g.hit + 2 * (size_t)id), h1 = __ldg(g.hit + 2 * (size_t)id + 1);
-                            depth_ = surfel_depth(h0, h1, ray, h1.z, vp.depth_thr, vp.normal_thr);
-                            hit_id = id;
-                            hit_dw = alpha * T;
-                            hit = true;
-                            opaque_lo = __int_as_float(0x7f800000);
-                        }
-                    }
-                    const float test_T = T * (1.f - alpha);
-                    if (test_T < T_thr) {
-                        // no colour is added any more; the pixel keeps scanning until it has an opaque hit
-                        if (hit) { done = true; pfx = FAR; }
-                        else T = test_T;
-                    } else {
-                        const float cw = alpha * T;
-                        const float4 col = lds128(REC_RGB(jb));
-                        C0 += col.x * cw; C1 += col.y * cw; C2 += col.z * cw;
-                        if (cw > cw_max) { cw_max = cw; j_cmax = j; }
-                        j_last = j;
-                        end_T = test_T;
-                        T = test_T;
-                    }
-                }
+                if (RTG_FWD_PRETEST(power, s0.z) && pair_alpha(power, s1.w, s0.w, alpha, au)) blend(j, jb, s0, power, alpha);
             }
+#endif
             if (__all_sync(FULL, done)) break;  // checked once per 32 entries: a finished warp skips visits cheaply
         }
         if (j_last >= 0) last_contributor = (uint32_t)(i * BATCH + j_last + 1);
