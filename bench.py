@@ -451,6 +451,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline(args, cam)
         line["extras"] = extras(dev, cam, t, leaves, step)
         line["optimize_step"] = line["extras"].pop("optimize_step", None)
+        line["map_optimize_step"] = line["extras"].pop("map_optimize_step", None)
         line["icp"] = icp_section(dev, cam)
         try:
             torch.cuda.empty_cache()
@@ -755,6 +756,98 @@ def extras(dev, cam, t, leaves, step):
                                "algorithmic_bytes_adam": 1652 * P, "note": "the Adam step alone is reported under extras.adam_fused_*"}
     except Exception as e:
         ex["optimize_step"] = {"error": repr(e)}
+    # the same iteration from RAW parameters, as Mapping.loss_update runs it (mapper.py:376-468): activations, attach
+    # regulariser, Adam over the six groups, confidence update -- fused (mapoptim.MapOptimizer) vs the reference's eager
+    # torch expressions around the same rasterizer
+    try:
+        import torch.nn.functional as F
+        from rtg_slam_b200 import _lib
+        from rtg_slam_b200.mapoptim import MapOptimizer
+        from rtg_slam_b200.rasterizer import visible_rows_only
+        with torch.no_grad():
+            op = leaves["opacity"].detach().clamp(1e-4, 1 - 1e-4)
+            raw = dict(xyz=leaves["xyz"].detach().clone(), features_dc=leaves["shs"].detach()[:, :1].clone(),
+                       features_rest=leaves["shs"].detach()[:, 1:].clone(), opacity=torch.log(op / (1 - op)),
+                       scaling=torch.log(leaves["scales"].detach()), rotation=leaves["rotations"].detach().clone())
+            init_stat = {"opacity": raw["opacity"].clone(), "scaling": raw["scaling"].clone(), "xyz": raw["xyz"].clone(),
+                         "rotation_raw": raw["rotation"].clone()}
+            init_stat["opacity"][::2] = 0.0  # half of the rows carry the attach term
+        lrs = dict(xyz=1e-6, f_dc=1e-6, f_rest=1e-6, opacity=0.0, scaling=1e-6, rotation=1e-6)
+        conf = torch.zeros(P, device=dev)
+        mo = MapOptimizer(raw["xyz"], raw["features_dc"], raw["features_rest"], raw["opacity"], raw["scaling"], raw["rotation"], lrs,
+                          confidence=conf)
+        mo.set_attach(init_stat)
+
+        def fused_step():
+            o = rend.render(vc, mo.gaussian_data())
+            loss, _ = l1_color_depth_loss(o, gt_c, gt_d)
+            with visible_rows_only():
+                loss.backward()
+            mo.step(radii=o["radii"])
+
+        pr = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+        topt = torch.optim.Adam([{"params": [pr["xyz"]], "lr": lrs["xyz"]}, {"params": [pr["features_dc"]], "lr": lrs["f_dc"]},
+                                 {"params": [pr["features_rest"]], "lr": lrs["f_rest"]}, {"params": [pr["opacity"]], "lr": 0.0},
+                                 {"params": [pr["scaling"]], "lr": lrs["scaling"]}, {"params": [pr["rotation"]], "lr": lrs["rotation"]}],
+                                lr=0.0, eps=1e-15)
+        conf2 = torch.zeros(P, device=dev)
+        amask = (torch.sigmoid(init_stat["opacity"]) < 0.9).squeeze()
+        l2 = lambda a_, b_: ((a_ - b_) ** 2).mean()
+
+        def eager_step():  # mapper.py:384-401,444-468 + the get_* properties of gaussian_pointcloud.py around our rasterizer
+            d = dict(xyz=pr["xyz"], opacity=torch.sigmoid(pr["opacity"]), scales=torch.exp(pr["scaling"]),
+                     rotations=F.normalize(pr["rotation"]), shs=torch.cat((pr["features_dc"], pr["features_rest"]), dim=1), normal=t["normal"])
+            attach = 1000 * (l2(pr["scaling"][amask], init_stat["scaling"][amask]) + l2(pr["xyz"][amask], init_stat["xyz"][amask])
+                             + l2(pr["rotation"][amask], init_stat["rotation_raw"][amask]))
+            loss, _ = l1_color_depth_loss(rend.render(vc, d), gt_c, gt_d)
+            (loss + attach).backward()
+            topt.step()
+            conf2[(pr["features_dc"].grad.abs() != 0).any(dim=-1).squeeze(-1)] += 1
+            topt.zero_grad(set_to_none=True)
+
+        def timed(fn, n=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(n):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a_.elapsed_time(b_) / n
+        ms_fused = timed(fused_step)
+        ms_eager = timed(eager_step)
+        # the fused step kernel alone
+        o = rend.render(vc, mo.gaussian_data())
+        l1_color_depth_loss(o, gt_c, gt_d)[0].backward()
+        keep = {k: getattr(mo, k).grad for k in ("xyz", "shs", "opacity", "scales", "rotations")}
+
+        def step_only():
+            for k, g_ in keep.items():
+                getattr(mo, k).grad = g_
+            mo.step(radii=o["radii"], zero_grad=False)
+        timed(step_only, 5)
+        _lib.profile_enable(True)
+        _lib.profile_read(reset=True)
+        for _ in range(30):
+            step_only()
+        prof = _lib.profile_read(reset=True)
+        _lib.profile_enable(False)
+        ms_step = prof["adam"][0] / max(1, prof["adam"][1])  # CUDA events around the kernel on its stream
+        vis_frac = float((o["radii"] > 0).float().mean())
+        step_bytes = P * (59 * 24 + 59 * 4 * vis_frac + 32 + 12 + 4 + 41)
+        ex["map_optimize_step"] = {
+            "workload": "BASELINE configs[2] from RAW parameters: 1 M Gaussians, 1920x1080, render + fused L1 loss + backward + "
+                        "activation backward + attach regulariser + Adam (6 groups) + confidence update",
+            "fused_ms_per_step": ms_fused, "fused_steps_per_s": 1e3 / ms_fused,
+            "eager_reference_flow_ms_per_step": ms_eager,
+            "eager_note": "the reference's torch expressions (exp / sigmoid / normalize / cat, masked l2 attach loss, "
+                          "torch.optim.Adam, confidence update) around THIS library's rasterizer and loss",
+            "map_adam_step_kernel_ms": ms_step, "map_adam_step_GBps": step_bytes / ms_step / 1e6,
+            "map_adam_step_algorithmic_bytes": int(step_bytes), "visible_fraction": vis_frac}
+    except Exception as e:
+        ex["map_optimize_step"] = {"error": repr(e)}
     return ex
 
 

@@ -102,6 +102,17 @@ int rtg_splat_backward(const RtgSplatView *view, int32_t P, int32_t M, const flo
                        float *dL_dcolors_precomp, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
                        float *dL_dcov3D, float *dL_dmeans2D, void *stream);
 
+/* rtg_splat_backward without the zero fill: only the gradient rows of Gaussians with radii > 0 are written, the
+ * others keep whatever the buffers held. For consumers that take `radii` themselves (rtg_map_adam_step): saves the
+ * 105 MB of zero stores per 1 M Gaussians that a dense consumer needs. Same arguments. */
+int rtg_splat_backward_visible(const RtgSplatView *view, int32_t P, int32_t M, const float *means3D, const float *shs,
+                               const float *colors_precomp, const float *scales, const float *rotations,
+                               const float *cov3D_precomp, const int32_t *radii, const void *geom_ws, const void *img_ws,
+                               const void *bin_ws, int64_t R_cap, const int32_t *counters, const float *final_T,
+                               const int32_t *hit_image, const float *dL_dcolor, const float *dL_ddepth, float *grad2d_scratch,
+                               float *dL_dmeans3D, float *dL_dsh, float *dL_dcolors_precomp, float *dL_dopacity,
+                               float *dL_dscales, float *dL_drotations, float *dL_dcov3D, float *dL_dmeans2D, void *stream);
+
 /* The same backward in two calls with the same argument list, for callers that put an exchange step between the
  * compositing backward and the per-Gaussian backward (tile-sharded multi-GPU rendering):
  *   rtg_splat_backward_render : zero-fill of the culled rows + backward of renderCUDA (backward.cu:808-1066); on return
@@ -195,6 +206,45 @@ typedef struct RtgAdamGroup {
 } RtgAdamGroup;
 int rtg_adam_step(const RtgAdamGroup *groups, int32_t n_groups, float beta1, float beta2, float eps, int32_t step,
                   void *stream);
+
+/* ---- fused map-parameter step ---------------------------------------------------------------
+ * One pass over the Gaussian map that replaces, per optimisation iteration of Mapping.loss_update
+ * (SLAM/multiprocess/mapper.py:376-468):
+ *   - the activation backward of get_scaling / get_rotation / get_opacity (torch.exp, F.normalize, torch.sigmoid;
+ *     SLAM/gaussian_pointcloud.py:16-25,511-523,574-581) and the slice backward of get_features' torch.cat,
+ *   - the gradient of the "attach" regulariser 1000 * (l2(_scaling) + l2(_xyz) + l2(_rotation)) on the rows with
+ *     attach_mask (mapper.py:384-401; l2_loss = mean of squares, utils/loss_utils.py:34-36),
+ *   - torch.optim.Adam(l, lr=0.0, eps=1e-15).step() over the six groups of parametrize (gaussian_pointcloud.py:245-284),
+ *   - `_confidence[(f_dc.grad.abs() != 0).any(-1)] += 1` (mapper.py:455-456),
+ *   - the activation forward (and get_normal, gaussian_pointcloud.py:539-550) for the next iteration's render.
+ * Gradients are the rasterizer's, i.e. with respect to the ACTIVATED tensors. With `radii` (the forward's output)
+ * rows with radii <= 0 are treated as zero gradient and never read, so the backward may be
+ * rtg_splat_backward_visible, which skips the zero fill of those rows. `sh` is ONE (P,16,3) block whose [:,0:1] /
+ * [:,1:] slices are _features_dc / _features_rest (no torch.cat). All pointers device memory; optional ones may be
+ * NULL: radii, attach_mask (+ xyz0, scaling0, rotation0), confidence, normal_out. */
+typedef struct RtgMapStep {
+    int32_t P;
+    int32_t step;                 /* Adam step number, >= 1 */
+    float *xyz, *sh, *opacity_raw, *scaling_raw, *rotation_raw;                 /* raw parameters, updated in place */
+    float *m_xyz, *m_sh, *m_opacity, *m_scaling, *m_rotation;                   /* exp_avg */
+    float *v_xyz, *v_sh, *v_opacity, *v_scaling, *v_rotation;                   /* exp_avg_sq */
+    const float *g_means3D, *g_sh, *g_opacity, *g_scales, *g_rotations;         /* rasterizer gradients */
+    const int32_t *radii;
+    const uint8_t *attach_mask;
+    const float *xyz0, *scaling0, *rotation0;                                   /* init_stat: _xyz, _scaling, _rotation (raw) */
+    float attach_weight;          /* 1000 in the reference */
+    int32_t attach_count;         /* number of rows with attach_mask (the means' denominators) */
+    float lr_xyz, lr_f_dc, lr_f_rest, lr_opacity, lr_scaling, lr_rotation;
+    float beta1, beta2, eps;
+    float *scales_out, *rotations_out, *opacities_out;                          /* activated values after the update */
+    float *normal_out;            /* (P,3) get_normal after the update */
+    float *confidence;            /* (P) float */
+} RtgMapStep;
+int rtg_map_adam_step(const RtgMapStep *step, void *stream);
+/* Activation forward only (initialisation): scales_out = exp(scaling_raw), rotations_out = normalize(rotation_raw),
+ * opacities_out = sigmoid(opacity_raw), normal_out = get_normal (may be NULL). */
+int rtg_map_activate(int32_t P, const float *scaling_raw, const float *rotation_raw, const float *opacity_raw,
+                     float *scales_out, float *rotations_out, float *opacities_out, float *normal_out, void *stream);
 
 /* ---- projective point-to-plane ICP ---------------------------------------------------------
  * Pyramid level: replaces nn.MaxPool2d(pool) (SLAM/icp.py:343-345,374) + compute_vertex_map

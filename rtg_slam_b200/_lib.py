@@ -34,6 +34,20 @@ class RtgAdamGroup(C.Structure):
     ]
 
 
+class RtgMapStep(C.Structure):
+    """include/rtg_splat_b200.h: RtgMapStep (field order is the ABI)."""
+    _fields_ = ([("P", C.c_int32), ("step", C.c_int32)]
+                + [(n, C.c_void_p) for n in ("xyz", "sh", "opacity_raw", "scaling_raw", "rotation_raw",
+                                             "m_xyz", "m_sh", "m_opacity", "m_scaling", "m_rotation",
+                                             "v_xyz", "v_sh", "v_opacity", "v_scaling", "v_rotation",
+                                             "g_means3D", "g_sh", "g_opacity", "g_scales", "g_rotations",
+                                             "radii", "attach_mask", "xyz0", "scaling0", "rotation0")]
+                + [("attach_weight", C.c_float), ("attach_count", C.c_int32)]
+                + [(n, C.c_float) for n in ("lr_xyz", "lr_f_dc", "lr_f_rest", "lr_opacity", "lr_scaling", "lr_rotation",
+                                            "beta1", "beta2", "eps")]
+                + [(n, C.c_void_p) for n in ("scales_out", "rotations_out", "opacities_out", "normal_out", "confidence")])
+
+
 class RtgIcpLevel(C.Structure):
     _fields_ = [("vertex0", C.c_void_p), ("normal0", C.c_void_p), ("vertex1", C.c_void_p), ("normal1", C.c_void_p),
                 ("H", C.c_int32), ("W", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
@@ -49,6 +63,7 @@ SIGNATURES = {
     "rtg_splat_workspace_bytes": (C.c_int, [_I32, _I32, _I32, _I64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "rtg_splat_forward": (C.c_int, [C.POINTER(RtgSplatView), _I32, _I32] + [_VP] * 8 + [_VP, _VP, _VP, _I64] + [_VP] * 8 + [_VP, _VP, _VP, _VP]),
     "rtg_splat_backward": (C.c_int, _BWD_ARGS),
+    "rtg_splat_backward_visible": (C.c_int, _BWD_ARGS),
     "rtg_splat_backward_render": (C.c_int, _BWD_ARGS),
     "rtg_splat_backward_finish": (C.c_int, _BWD_ARGS),
     "rtg_splat_geom_layout": (C.c_int, [_I32] + [C.POINTER(C.c_size_t)] * 4),
@@ -58,6 +73,8 @@ SIGNATURES = {
     "rtg_splat_backward_finish_shard": (C.c_int, [_I32, _I32] + _BWD_ARGS),
     "rtg_splat_mark_visible": (C.c_int, [_I32, _VP, _VP, _VP, _VP, _VP]),
     "rtg_adam_step": (C.c_int, [C.POINTER(RtgAdamGroup), _I32, _F, _F, _F, _I32, _VP]),
+    "rtg_map_adam_step": (C.c_int, [C.POINTER(RtgMapStep), _VP]),
+    "rtg_map_activate": (C.c_int, [_I32] + [_VP] * 8),
     "rtg_icp_workspace_bytes": (C.c_size_t, [_I32, _I32]),
     "rtg_icp_build_level": (C.c_int, [_VP, _I32, _I32, _I32, _F, _F, _F, _F, _VP, _VP, _VP, _VP]),
     "rtg_icp_solve_level": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _F, _F, _F, _F, _F, _I32, _VP, _VP, _VP, _VP]),

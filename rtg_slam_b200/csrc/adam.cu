@@ -16,14 +16,6 @@ struct AdamArgs {
     float beta1, beta2, eps, bc1, bc2_sqrt;
 };
 
-__device__ __forceinline__ void adam_one(float &p, const float g, float &m, float &v, const float lr_over_bc1, const float beta1,
-                                         const float beta2, const float eps, const float bc2_sqrt) {
-    m = m + (g - m) * (1.f - beta1);           // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * beta2 + (1.f - beta2) * g * g;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    p = p - lr_over_bc1 * (m / denom);         // param.addcdiv_(exp_avg, denom, value=-step_size)
-}
-
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     const RtgAdamGroup grp = a.g[blockIdx.y];
     if (grp.grad == nullptr || grp.numel <= 0) return;

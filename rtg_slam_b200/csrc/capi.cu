@@ -14,6 +14,9 @@
 
 namespace rtg {
 int launch_adam(const RtgAdamGroup *groups, int n_groups, float beta1, float beta2, float eps, int step, cudaStream_t s);
+void launch_map_adam_step(const RtgMapStep &st, cudaStream_t s);
+void launch_map_activate(int P, const float *scaling_raw, const float *rotation_raw, const float *opacity_raw, float *scales_out,
+                         float *rotations_out, float *opacities_out, float *normal_out, cudaStream_t s);
 size_t icp_ws_bytes();
 void launch_icp_build_level(const float *depth, int H, int W, int pool, float fx, float fy, float cx, float cy, float *vertex,
                             float *normal, void *ws, cudaStream_t s);
@@ -351,7 +354,9 @@ static int splat_backward_impl(int phase, int32_t p_begin, int32_t p_end, const 
     // backward reads the same device counters the forward wrote.
     // fork: the zero-fill of the culled rows only depends on the forward; it streams to HBM on a side stream while
     // the compute-bound render backward runs, and joins before the call's work on `s` ends
-    if (phase != 2) {
+    if (phase == 3) {  // visible rows only: no zero fill
+        rtg::launch_render_bwd(vp, g, b, img, counters, final_T, hit_image, dL_dcolor, dL_ddepth, grad2d_scratch, s);
+    } else if (phase != 2) {
         SideStream *ss = side_stream();
         std::unique_lock<std::mutex> side_lock;
         if (ss) side_lock = std::unique_lock<std::mutex>(ss->use);
@@ -389,6 +394,7 @@ static int splat_backward_impl(int phase, int32_t p_begin, int32_t p_end, const 
         final_T, hit_image, dL_dcolor, dL_ddepth, grad2d_scratch, dL_dmeans3D, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales, \
         dL_drotations, dL_dcov3D, dL_dmeans2D, stream
 int rtg_splat_backward(RTG_BWD_PARAMS) { return splat_backward_impl(0, 0, P, RTG_BWD_ARGS); }
+int rtg_splat_backward_visible(RTG_BWD_PARAMS) { return splat_backward_impl(3, 0, P, RTG_BWD_ARGS); }
 int rtg_splat_backward_render(RTG_BWD_PARAMS) { return splat_backward_impl(1, 0, P, RTG_BWD_ARGS); }
 int rtg_splat_backward_finish(RTG_BWD_PARAMS) { return splat_backward_impl(2, 0, P, RTG_BWD_ARGS); }
 int rtg_splat_backward_render_shard(int32_t p_begin, int32_t p_end, RTG_BWD_PARAMS) {
@@ -415,6 +421,40 @@ int rtg_adam_step(const RtgAdamGroup *groups, int32_t n_groups, float beta1, flo
             return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_adam_step: NULL param / state pointer");
     rtg::launch_adam(groups, n_groups, beta1, beta2, eps, step, reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_adam_step");
+}
+
+int rtg_map_adam_step(const RtgMapStep *st, void *stream) {
+    if (!st) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_adam_step: NULL step");
+    if (st->P < 0 || st->step < 1) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_adam_step: P must be >= 0 and step >= 1");
+    if (st->P == 0) return RTG_OK;
+    const void *need[] = {st->xyz, st->sh, st->opacity_raw, st->scaling_raw, st->rotation_raw, st->m_xyz, st->m_sh, st->m_opacity,
+                          st->m_scaling, st->m_rotation, st->v_xyz, st->v_sh, st->v_opacity, st->v_scaling, st->v_rotation,
+                          st->g_means3D, st->g_sh, st->g_opacity, st->g_scales, st->g_rotations, st->scales_out, st->rotations_out,
+                          st->opacities_out};
+    for (const void *q : need)
+        if (!q) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_adam_step: NULL parameter / state / gradient / output pointer");
+    const void *al16[] = {st->sh, st->m_sh, st->v_sh, st->g_sh, st->rotation_raw, st->m_rotation, st->v_rotation, st->g_rotations,
+                          st->rotations_out, st->rotation0};
+    for (const void *q : al16)
+        if (((uintptr_t)q) & 15) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_adam_step: sh / rotation tensors must be 16-byte aligned");
+    if (st->attach_mask && (!st->xyz0 || !st->scaling0 || !st->rotation0))
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_adam_step: attach_mask needs xyz0, scaling0 and rotation0");
+    if (st->attach_mask && st->attach_count < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_adam_step: attach_count < 0");
+    rtg::launch_map_adam_step(*st, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_map_adam_step");
+}
+
+int rtg_map_activate(int32_t P, const float *scaling_raw, const float *rotation_raw, const float *opacity_raw, float *scales_out,
+                     float *rotations_out, float *opacities_out, float *normal_out, void *stream) {
+    if (P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_activate: P < 0");
+    if (P == 0) return RTG_OK;
+    if (!scaling_raw || !rotation_raw || !opacity_raw || !scales_out || !rotations_out || !opacities_out)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_activate: NULL pointer");
+    if ((((uintptr_t)rotation_raw) | ((uintptr_t)rotations_out)) & 15)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_activate: rotation tensors must be 16-byte aligned");
+    rtg::launch_map_activate(P, scaling_raw, rotation_raw, opacity_raw, scales_out, rotations_out, opacities_out, normal_out,
+                             reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_map_activate");
 }
 
 size_t rtg_icp_workspace_bytes(int32_t H, int32_t W) {

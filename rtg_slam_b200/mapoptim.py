@@ -1,0 +1,229 @@
+"""Fused parametrize + activations + attach regulariser + Adam for the Gaussian map.
+
+What the reference does per optimisation iteration around the rasterizer (`Mapping.loss_update`,
+SLAM/multiprocess/mapper.py:376-468; `GaussianPointCloud.parametrize` and the activation properties,
+SLAM/gaussian_pointcloud.py:245-284,511-523,574-581):
+
+    get_scaling = exp(_scaling); get_rotation = normalize(_rotation); get_opacity = sigmoid(_opacity)
+    get_features = cat(_features_dc, _features_rest); get_normal                      (forward, ~15 launches)
+    attach_loss = 1000 * (l2(_scaling[m], s0[m]) + l2(_xyz[m], x0[m]) + l2(_rotation[m], r0[m]))
+    (loss + attach_loss).backward()        -> the same nodes backward, cat/slice/mask-index backward
+    optimizer.step()                       -> torch.optim.Adam(l, lr=0.0, eps=1e-15): 6 groups
+    _confidence[(f_dc.grad.abs() != 0).any(-1)] += 1
+
+`MapOptimizer` keeps the raw parameters and the Adam moments, exposes the ACTIVATED tensors as autograd leaves for
+`Renderer.render`, and `step()` does all of the above except the image loss in ONE kernel (`rtg_map_adam_step`):
+activation backward, attach gradient, Adam, confidence, activation forward + get_normal for the next iteration.
+With `rasterizer.visible_rows_only()` around the backward and `step(radii=...)`, culled rows are neither zero-filled
+nor read.
+
+    opt = MapOptimizer.from_pointcloud(pointcloud, update_args)        # replaces parametrize + torch.optim.Adam
+    opt.set_attach(init_stat)                                          # mapper.py:384-401
+    for it in range(iters):
+        out = renderer.render(frame, opt.gaussian_data())
+        loss, parts = mapping_loss(out, image_input, render_mask, ...)
+        with visible_rows_only():
+            loss.backward()
+        opt.step(radii=out["radii"])                                   # also zero_grad(set_to_none=True)
+    opt.write_back(pointcloud)                                         # replaces pointcloud.detach()
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RtgMapStep, check
+
+GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")  # order of parametrize's list
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class MapOptimizer:
+    def __init__(self, xyz, features_dc, features_rest, opacity, scaling, rotation, lrs, betas=(0.9, 0.999), eps=1e-15,
+                 confidence=None, attach_weight=1000.0):
+        """Raw parameter tensors as GaussianPointCloud holds them: `_xyz (P,3)`, `_features_dc (P,1,3)`,
+        `_features_rest (P,15,3)`, `_opacity (P,1)`, `_scaling (P,3)`, `_rotation (P,4)` (values are copied).
+        `lrs`: dict by GROUPS (or a 6-sequence in that order). `confidence`: optional (P,) / (P,1) float tensor, updated
+        in place by step()."""
+        dev = xyz.device
+        if dev.type != "cuda":
+            raise TypeError("MapOptimizer: parameters must be CUDA tensors (there is no CPU path)")
+        P = xyz.shape[0]
+        for name, t, shape in (("xyz", xyz, (P, 3)), ("features_dc", features_dc, (P, 1, 3)), ("features_rest", features_rest, (P, 15, 3)),
+                               ("opacity", opacity, (P, 1)), ("scaling", scaling, (P, 3)), ("rotation", rotation, (P, 4))):
+            if t.dtype != torch.float32 or t.device != dev:
+                raise TypeError(f"MapOptimizer: {name} must be float32 on {dev}")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"MapOptimizer: {name} must have shape {shape}, got {tuple(t.shape)} "
+                                 "(spherical harmonics of degree 3: 1 + 15 coefficients)")
+        if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0) or eps < 0:
+            raise ValueError("MapOptimizer: invalid betas / eps")
+        self.device, self.P = dev, P
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
+        self.lrs = dict(zip(GROUPS, lrs)) if not isinstance(lrs, dict) else {k: float(lrs[k]) for k in GROUPS}
+        self.attach_weight = float(attach_weight)
+        self.step_count = 0
+        with torch.no_grad():
+            # rasterizer inputs that are raw parameters themselves
+            self.xyz = xyz.detach().clone().contiguous().requires_grad_(True)
+            self.shs = torch.cat([features_dc.detach(), features_rest.detach()], dim=1).contiguous().requires_grad_(True)  # once
+            # raw parameters behind an activation
+            self.opacity_raw = opacity.detach().clone().contiguous()
+            self.scaling_raw = scaling.detach().clone().contiguous()
+            self.rotation_raw = rotation.detach().clone().contiguous()
+            # activated leaves, rewritten by every step
+            self.opacity = torch.empty_like(self.opacity_raw)
+            self.scales = torch.empty_like(self.scaling_raw)
+            self.rotations = torch.empty_like(self.rotation_raw)
+            self.normal = torch.empty((P, 3), dtype=torch.float32, device=dev)
+            check(_lib.lib().rtg_map_activate(P, _p(self.scaling_raw), _p(self.rotation_raw), _p(self.opacity_raw), _p(self.scales),
+                                              _p(self.rotations), _p(self.opacity), _p(self.normal), self._stream()), "rtg_map_activate")
+        for t in (self.opacity, self.scales, self.rotations):
+            t.requires_grad_(True)
+        self.state = {k: (torch.zeros_like(t), torch.zeros_like(t)) for k, t in
+                      (("xyz", self.xyz), ("sh", self.shs), ("opacity", self.opacity_raw), ("scaling", self.scaling_raw),
+                       ("rotation", self.rotation_raw))}
+        if confidence is not None and (confidence.dtype != torch.float32 or confidence.numel() != P or not confidence.is_contiguous()
+                                       or confidence.device != dev):
+            raise TypeError("MapOptimizer: confidence must be a contiguous float32 tensor with one element per Gaussian")
+        self.confidence = confidence
+        self._attach = None
+        self._st = None
+
+    # ------------------------------------------------------------------ construction from / write-back to the reference's store
+    @classmethod
+    def from_pointcloud(cls, pc, update_args, lr_scale=None, **kw):
+        """`pc`: a GaussianPointCloud; `update_args`: the namespace parametrize reads (position_lr, feature_lr, opacity_lr,
+        scaling_lr, rotation_lr). `lr_scale`: optional dict of per-group multipliers (global optimisation scales xyz /
+        scaling / rotation, mapper.py:606-615)."""
+        lrs = {"xyz": update_args.position_lr, "f_dc": update_args.feature_lr, "f_rest": update_args.feature_lr / 20.0,
+               "opacity": update_args.opacity_lr, "scaling": update_args.scaling_lr, "rotation": update_args.rotation_lr}
+        for k, v in (lr_scale or {}).items():
+            lrs[k] *= v
+        conf = getattr(pc, "_confidence", None)
+        return cls(pc._xyz, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling, pc._rotation, lrs,
+                   confidence=None if conf is None else conf.view(-1), **kw)
+
+    def write_back(self, pc):
+        """The optimised raw parameters into a GaussianPointCloud, detached (what `pointcloud.detach()` leaves behind,
+        gaussian_pointcloud.py:306-313). `_features_dc` / `_features_rest` become views of one (P,16,3) block."""
+        pc._xyz = self.xyz.detach()
+        pc._features_dc = self.features_dc
+        pc._features_rest = self.features_rest
+        pc._opacity = self.opacity_raw
+        pc._scaling = self.scaling_raw
+        pc._rotation = self.rotation_raw
+        return pc
+
+    # ------------------------------------------------------------------ views
+    @property
+    def features_dc(self):
+        return self.shs.detach()[:, :1]
+
+    @property
+    def features_rest(self):
+        return self.shs.detach()[:, 1:]
+
+    def gaussian_data(self):
+        """The dict `Renderer.render` takes (SLAM/render.py:93-98; what Mapping.get_render_output builds from the
+        pointcloud's get_* properties). The tensors are autograd leaves: backward leaves their `.grad` for step()."""
+        return {"xyz": self.xyz, "opacity": self.opacity, "scales": self.scales, "rotations": self.rotations, "shs": self.shs,
+                "normal": self.normal}
+
+    # ------------------------------------------------------------------ attach regulariser
+    def set_attach(self, init_stat):
+        """`init_stat`: dict with "opacity" (raw), "scaling", "xyz", "rotation_raw" as mapper.py:617-622 builds it; the mask
+        is sigmoid(opacity) < 0.9 (mapper.py:384-385). One host read of the mask count, once per optimisation call. None
+        removes the term."""
+        self._st = None
+        if init_stat is None:
+            self._attach = None
+            return
+        mask = (torch.sigmoid(init_stat["opacity"]) < 0.9).reshape(-1)
+        if mask.numel() != self.P:
+            raise ValueError("MapOptimizer.set_attach: init_stat has a different number of Gaussians")
+        count = int(mask.sum().item())
+        self._attach = None if count == 0 else dict(
+            mask=mask.to(torch.uint8).contiguous(), count=count, xyz0=init_stat["xyz"].detach().float().contiguous(),
+            scaling0=init_stat["scaling"].detach().float().contiguous(), rotation0=init_stat["rotation_raw"].detach().float().contiguous())
+
+    def attach_loss(self):
+        """Value of the regulariser (for reporting; its gradient is applied inside step())."""
+        if self._attach is None:
+            return torch.zeros((), device=self.device)
+        m = self._attach["mask"].bool()
+
+        def l2(a, b):
+            return ((a[m] - b[m]) ** 2).mean()
+        with torch.no_grad():
+            return self.attach_weight * (l2(self.scaling_raw, self._attach["scaling0"]) + l2(self.xyz, self._attach["xyz0"])
+                                         + l2(self.rotation_raw, self._attach["rotation0"]))
+
+    # ------------------------------------------------------------------ the step
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _step_struct(self):
+        """The argument block of rtg_map_adam_step; everything but the gradients, radii and the step number is fixed
+        between set_attach calls, so it is filled once."""
+        if self._st is None:
+            st = RtgMapStep()
+            st.P = self.P
+            st.xyz, st.sh, st.opacity_raw = _p(self.xyz), _p(self.shs), _p(self.opacity_raw)
+            st.scaling_raw, st.rotation_raw = _p(self.scaling_raw), _p(self.rotation_raw)
+            for key in ("xyz", "sh", "opacity", "scaling", "rotation"):
+                m, v = self.state[key]
+                setattr(st, "m_" + key, _p(m))
+                setattr(st, "v_" + key, _p(v))
+            if self._attach is not None:
+                a = self._attach
+                st.attach_mask, st.xyz0, st.scaling0, st.rotation0 = _p(a["mask"]), _p(a["xyz0"]), _p(a["scaling0"]), _p(a["rotation0"])
+                st.attach_weight, st.attach_count = self.attach_weight, a["count"]
+            st.lr_xyz, st.lr_f_dc, st.lr_f_rest = self.lrs["xyz"], self.lrs["f_dc"], self.lrs["f_rest"]
+            st.lr_opacity, st.lr_scaling, st.lr_rotation = self.lrs["opacity"], self.lrs["scaling"], self.lrs["rotation"]
+            st.beta1, st.beta2, st.eps = self.betas[0], self.betas[1], self.eps
+            st.scales_out, st.rotations_out, st.opacities_out = _p(self.scales), _p(self.rotations), _p(self.opacity)
+            st.normal_out, st.confidence = _p(self.normal), _p(self.confidence)
+            self._st = st
+        return self._st
+
+    def zero_grad(self, set_to_none=True):
+        for t in (self.xyz, self.shs, self.opacity, self.scales, self.rotations):
+            if t.grad is not None:
+                if set_to_none:
+                    t.grad = None
+                else:
+                    t.grad.zero_()
+
+    @torch.no_grad()
+    def step(self, radii=None, zero_grad=True):
+        """One Adam step from the `.grad` of the five rasterizer inputs. `radii`: the forward's radii (int32, P) -- required
+        when the backward ran under `rasterizer.visible_rows_only()`: rows with radii <= 0 then count as zero gradient and
+        are not read. Rewrites the activated tensors (and `normal`) in place and, by default, drops the gradients."""
+        grads = {}
+        for name, t in (("xyz", self.xyz), ("shs", self.shs), ("opacity", self.opacity), ("scales", self.scales),
+                        ("rotations", self.rotations)):
+            g = t.grad
+            if g is None:
+                raise RuntimeError(f"MapOptimizer.step: '{name}' has no gradient (run loss.backward() on a render of gaussian_data())")
+            if g.dtype != torch.float32 or g.device != self.device:
+                raise TypeError(f"MapOptimizer.step: gradient of '{name}' must be float32 on {self.device}")
+            grads[name] = g if g.is_contiguous() else g.contiguous()
+        if radii is not None and (radii.dtype != torch.int32 or radii.numel() != self.P or radii.device != self.device
+                                  or not radii.is_contiguous()):
+            raise TypeError("MapOptimizer.step: radii must be the rasterizer's contiguous int32 (P,) output")
+        self.step_count += 1
+        st = self._step_struct()
+        st.step = self.step_count
+        st.g_means3D, st.g_sh, st.g_opacity = _p(grads["xyz"]), _p(grads["shs"]), _p(grads["opacity"])
+        st.g_scales, st.g_rotations = _p(grads["scales"]), _p(grads["rotations"])
+        st.radii = _p(radii)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().rtg_map_adam_step(C.byref(st), self._stream()), "rtg_map_adam_step")
+        if zero_grad:
+            self.zero_grad(set_to_none=True)

@@ -352,7 +352,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _ptr(g_means), _ptr(g_sh), _ptr(g_colors), _ptr(g_opac), _ptr(g_scales), _ptr(g_rot), _ptr(g_cov), None,
                     C.c_void_p(stream))
             hook = _GRAD_RECORD_HOOK[0]
-            if hook is None:
+            if hook is None and _VISIBLE_ROWS_ONLY[0]:
+                check(L.rtg_splat_backward_visible(*args), "rtg_splat_backward_visible")
+            elif hook is None:
                 check(L.rtg_splat_backward(*args), "rtg_splat_backward")
             else:
                 # exchange step between the compositing backward and the per-Gaussian backward (tile-sharded frames)
@@ -382,6 +384,28 @@ class grad_buffers:
 
     def __exit__(self, *exc):
         _GRAD_BUFFERS[0] = self.prev
+        return False
+
+
+# When set, the backward leaves the gradient rows of culled Gaussians (radii <= 0) unwritten (see `visible_rows_only`).
+_VISIBLE_ROWS_ONLY = [False]
+
+
+class visible_rows_only:
+    """Context manager: while active, the rasterizer backward writes only the gradient rows of Gaussians with radii > 0
+    and leaves the others UNSPECIFIED (not zero) -- it skips the zero fill that a dense consumer needs (105 MB of stores
+    per 1 M Gaussians). For consumers that mask by `radii` themselves: `mapoptim.MapOptimizer.step(radii=...)`."""
+
+    def __init__(self, enabled=True):
+        self.enabled, self.prev = bool(enabled), None
+
+    def __enter__(self):
+        self.prev = _VISIBLE_ROWS_ONLY[0]
+        _VISIBLE_ROWS_ONLY[0] = self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _VISIBLE_ROWS_ONLY[0] = self.prev
         return False
 
 

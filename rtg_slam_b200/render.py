@@ -114,4 +114,5 @@ class Renderer:
             "color_hit_weight": color_hit_weight,
             "depth_hit_weight": depth_hit_weight,
             "T_map": T_map,
+            "radii": res[7],  # not in the reference's dict: the visibility mapoptim.MapOptimizer.step(radii=...) takes
         }

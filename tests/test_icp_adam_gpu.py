@@ -137,7 +137,9 @@ def test_renderer_api(cuda_device):
     t = {k: torch.from_numpy(v).to(dev) for k, v in g.items()}
     data = dict(xyz=t["xyz"], opacity=t["opacity"], scales=t["scales"], rotations=t["rotations"], shs=t["shs"], normal=t["normal"])
     out = Renderer(args).render(vc, data)
-    assert set(out) == {"render", "depth", "normal", "color_index_map", "depth_index_map", "color_hit_weight", "depth_hit_weight", "T_map"}
+    # the reference's keys (SLAM/render.py:135-145) plus "radii" (the visibility MapOptimizer.step takes)
+    assert set(out) == {"render", "depth", "normal", "color_index_map", "depth_index_map", "color_hit_weight", "depth_hit_weight", "T_map",
+                        "radii"}
     idx = out["depth_index_map"][0]
     ref = torch.zeros_like(out["render"])
     ref[:, idx > -1] = t["normal"][idx[idx > -1].long()].permute(1, 0)  # the reference's own expression (render.py:130-133)

@@ -10,7 +10,7 @@ print({k:d[k] for k in ("value","ms_per_step","n_gpus")}, "e2e", d["e2e"]["value
 print({k:round(v["ms"],4) for k,v in d["roofline"]["per_kernel"].items()})
 print("parity", d.get("parity"))
 print("icp", {k:v for k,v in (d.get("icp") or {}).items() if k in ("value","ms_per_predict_pose","device_ms_per_predict_pose","vs_reference_cuda","vs_reference_cpu","pose_diff_vs_reference","reference_cuda","reference_cpu")})
-print("optimize_step", d.get("optimize_step"))
+print("optimize_step", d.get("optimize_step")); print("map_optimize_step", d.get("map_optimize_step"))
 ex=d.get("extras",{})
 print("ref_cuda", ex.get("reference_cuda")); print("sharded", ex.get("gaussian_sharded_4M")); print("cpu", d.get("cpu_baseline"))
 PY
