@@ -329,6 +329,16 @@ int rtg_loss_mapping(const float *render, const float *depth, const float *rende
                      int32_t gt_channels_last, float color_weight, float depth_weight, float normal_weight, float depth_error_max,
                      float *dL_dcolor, float *dL_ddepth, float *dL_dnormal, float *loss_out, void *ws, void *stream);
 
+/* SSIM term of Mapping.loss_update (mapper.py:411-415: ssim_loss = 1 - ssim(render, gt), evaluated only without a render
+ * mask) with ssim of utils/loss_utils.py:40-100: 11x11 Gaussian window (sigma 1.5, one per channel), zero padding,
+ * C1 = 0.01^2, C2 = 0.03^2, mean over all C*H*W entries of the ssim map. img1, img2: (C,H,W).
+ * loss_out: 2 device floats {1 - mean(ssim_map), mean(ssim_map)}; dL_dimg1 (C,H,W) = d loss_out[0] / d img1, or NULL for the
+ * value only. Replaces five grouped 11x11 convolutions, ~15 elementwise kernels and their autograd twins by three launches;
+ * the mean is reduced in a fixed order (bit-reproducible). ws: rtg_ssim_workspace_bytes(C, H, W) bytes. */
+size_t rtg_ssim_workspace_bytes(int32_t C, int32_t H, int32_t W);
+int rtg_ssim_loss(const float *img1, const float *img2, int32_t C, int32_t H, int32_t W, float *dL_dimg1, float *loss_out, void *ws,
+                  void *stream);
+
 /* render_normal of Renderer.render (SLAM/render.py:130-133): out (3,H,W) = normal[depth_index] where the index is
  * > -1, zeros elsewhere; normal is (P,3). */
 int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream);

@@ -85,6 +85,8 @@ SIGNATURES = {
     "rtg_loss_workspace_bytes": (C.c_size_t, []),
     "rtg_loss_l1": (C.c_int, [_VP] * 6 + [_I32, _I32, _I32, _F, _F, _F, _VP, _VP, _VP, _VP, _VP]),
     "rtg_loss_mapping": (C.c_int, [_VP] * 8 + [_I32, _I32, _I32, _F, _F, _F, _F, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rtg_ssim_workspace_bytes": (C.c_size_t, [_I32, _I32, _I32]),
+    "rtg_ssim_loss": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP]),
     "rtg_normal_map": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP]),
     "rtg_frame_preprocess": (C.c_int, [_VP, _I32, _I32, _I32, _I32] + [_F] * 9 + [_VP] * 7),
     "rtg_accumulate_gaussian_error": (C.c_int, [_I32, _I32, _I32] + [_VP] * 5 + [_F, _F, _F, _I32] + [_VP] * 6),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtg_splat_b200.so")
-SOURCES = ["capi.cu", "preprocess.cu", "binning.cu", "render.cu", "adam.cu", "icp.cu", "loss.cu", "mapstats.cu", "frameprep.cu", "mapsurgery.cu", "mapstep.cu"]
+SOURCES = ["capi.cu", "preprocess.cu", "binning.cu", "render.cu", "adam.cu", "icp.cu", "loss.cu", "ssim.cu", "mapstats.cu", "frameprep.cu", "mapsurgery.cu", "mapstep.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

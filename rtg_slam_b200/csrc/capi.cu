@@ -26,6 +26,9 @@ void launch_icp_solve_level(const float *v0, const float *n0, const float *v1, c
 void launch_icp_p2p(const float *v_t0, const float *v_t1, const float *n_t0, int H, int W, const float *pose, float *loss,
                     void *ws, cudaStream_t s);
 size_t loss_ws_bytes();
+size_t ssim_ws_bytes(int C, int H, int W);
+void launch_ssim_loss(const float *img1, const float *img2, int C, int H, int W, float *dL_dimg1, float *loss_out, void *ws,
+                      cudaStream_t s);
 void launch_loss_l1(const float *render, const float *depth, const int *depth_index, const float *gt_color, const float *gt_depth,
                     const uint8_t *mask, int H, int W, int channels_last, float color_weight, float depth_weight,
                     float depth_error_max, float *dL_dcolor, float *dL_ddepth, float *loss_out, void *ws, cudaStream_t s);
@@ -574,6 +577,19 @@ int rtg_loss_mapping(const float *render, const float *depth, const float *rende
                              color_weight, depth_weight, normal_weight, depth_error_max, dL_dcolor, dL_ddepth, dL_dnormal, loss_out, ws,
                              reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_loss_mapping");
+}
+
+size_t rtg_ssim_workspace_bytes(int32_t C, int32_t H, int32_t W) {
+    if (C <= 0 || H <= 0 || W <= 0) return 0;
+    return rtg::ssim_ws_bytes(C, H, W);
+}
+
+int rtg_ssim_loss(const float *img1, const float *img2, int32_t C, int32_t H, int32_t W, float *dL_dimg1, float *loss_out, void *ws,
+                  void *stream) {
+    if (!img1 || !img2 || !loss_out || !ws || C <= 0 || C > 65535 || H <= 0 || W <= 0 || (H + 15) / 16 > 65535)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_ssim_loss: bad arguments");
+    rtg::launch_ssim_loss(img1, img2, C, H, W, dL_dimg1, loss_out, ws, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_ssim_loss");
 }
 
 int rtg_normal_map(const float *normal, const int32_t *depth_index, int32_t H, int32_t W, float *out, void *stream) {

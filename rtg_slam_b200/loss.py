@@ -128,11 +128,57 @@ class _FusedMapping(torch.autograd.Function):
         return (saved[0] * grad_loss, saved[1] * grad_loss, gn) + (None,) * 9
 
 
+_SSIM_WS = {}
+
+
+class _FusedSsim(torch.autograd.Function):
+    """1 - ssim(img1, img2) of utils/loss_utils.py:40-100 (11x11 Gaussian window, sigma 1.5, zero padding, mean) and its
+    gradient w.r.t. img1 from three kernels (rtg_ssim_loss) instead of five grouped convolutions + ~15 elementwise kernels
+    and their autograd twins. img2 (the measured frame) gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, img1, img2):
+        L = _lib.lib()
+        if img1.dim() != 3 or img1.shape != img2.shape:
+            raise ValueError("ssim_loss: img1 and img2 must both be (C,H,W)")
+        for name, t in (("img1", img1), ("img2", img2)):
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise TypeError(f"{name} must be a CUDA float32 tensor")
+        dev = img1.device
+        Cn, H, W = img1.shape
+        a, b = img1.contiguous(), img2.contiguous()
+        need = int(L.rtg_ssim_workspace_bytes(Cn, H, W))
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        ws = _SSIM_WS.get(idx)
+        if ws is None or ws.numel() < need:
+            ws = _SSIM_WS[idx] = torch.empty(need, dtype=torch.uint8, device=dev)
+        want_grad = ctx.needs_input_grad[0]
+        g = torch.empty_like(a) if want_grad else None
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        check(L.rtg_ssim_loss(_p(a), _p(b), Cn, H, W, _p(g), _p(out), _p(ws), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+              "rtg_ssim_loss")
+        if want_grad:
+            ctx.save_for_backward(g)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (g,) = ctx.saved_tensors
+        return g * grad_loss, None
+
+
+def ssim_loss(img1, img2):
+    """`1 - ssim(img1, img2)` as Mapping.loss_update evaluates it (SLAM/multiprocess/mapper.py:411-415, utils/loss_utils.py:50-100);
+    img1, img2: (C,H,W) CUDA float32. Differentiable w.r.t. img1."""
+    return _FusedSsim.apply(img1, img2)
+
+
 def _ssim_term(img1, img2, window_size=11):
-    """1 - ssim(img1, img2) exactly as utils/loss_utils.py:40-80 (11x11 Gaussian window, sigma 1.5, zero padding, mean)."""
+    """TEST REFERENCE, not used by `mapping_loss`: 1 - ssim(img1, img2) with the reference's own torch expressions
+    (utils/loss_utils.py:40-100: 11x11 Gaussian window, sigma 1.5, zero padding, mean)."""
     import torch.nn.functional as F
     ch = img1.size(-3)
-    x = torch.arange(window_size, dtype=torch.float32, device=img1.device)
+    x = torch.arange(window_size, dtype=img1.dtype, device=img1.device)
     g = torch.exp(-((x - window_size // 2) ** 2) / float(2 * 1.5 ** 2))
     g = (g / g.sum()).unsqueeze(1)
     window = (g @ g.t()).unsqueeze(0).unsqueeze(0).expand(ch, 1, window_size, window_size).contiguous()
@@ -153,8 +199,8 @@ def mapping_loss(render_output, image_input, render_mask=None, color_weight=0.8,
     """The image-space part of `Mapping.loss_update` (SLAM/multiprocess/mapper.py:402-451): colour L1 on the render mask,
     depth L1 on the valid mask, cosine normal loss, and -- only without a render mask, as in the reference -- the SSIM
     term. `render_output`: dict of Renderer.render; `image_input`: dict with "color_map" (H,W,3), "depth_map" (H,W[,1]),
-    "normal_map" (H,W,3). Colour, depth and normal terms and their gradients come from two fused kernels; the SSIM term
-    (which the shipped flows never reach: both call sites pass a render mask) is the reference's own formula in torch.
+    "normal_map" (H,W,3). Colour, depth and normal terms and their gradients come from two fused kernels, the SSIM term
+    (which the shipped flows never reach: both call sites pass a render mask) from three more (`ssim_loss`).
     Returns (total_loss, parts): parts is a device tensor {total, colour, depth, n_depth, normal, n_normal, ssim, 0} --
     read it back once with `report_losses` instead of six `.item()` calls (mapper.py:459-466)."""
     nrm = render_output.get("normal") if normal_weight > 0 else None
@@ -165,7 +211,7 @@ def mapping_loss(render_output, image_input, render_mask=None, color_weight=0.8,
     if render_mask is None and ssim_weight > 0:
         gt = image_input["color_map"]
         gt = gt.permute(2, 0, 1) if gt.shape[-1] == 3 and gt.dim() == 3 and gt.shape[0] != 3 else gt
-        ssim_l = _ssim_term(render_output["render"], gt)
+        ssim_l = ssim_loss(render_output["render"], gt)
         loss = loss + ssim_weight * ssim_l
         parts = parts.clone()
         parts[6] = ssim_l.detach()

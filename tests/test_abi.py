@@ -72,6 +72,10 @@ def test_side_entry_points_validate_before_touching_cuda():
     assert b"rtg_frame_preprocess" in L.rtg_last_error()
     assert L.rtg_loss_l1(*(nul * 6), 16, 16, 0, 0.8, 1.0, 0.1, *(nul * 5)) == -1
     assert L.rtg_normal_map(None, None, 16, 16, None, None) == -1
+    assert L.rtg_ssim_loss(None, None, 3, 16, 16, None, None, None, None) == -1 and b"rtg_ssim_loss" in L.rtg_last_error()
+    # partial sums (one double per 16x16 tile and channel, 256-byte aligned) + three derivative maps
+    assert L.rtg_ssim_workspace_bytes(3, 680, 1200) == ((3 * 43 * 75 * 8 + 255) // 256) * 256 + 3 * 3 * 680 * 1200 * 4
+    assert L.rtg_ssim_workspace_bytes(0, 16, 16) == 0
     for fn in (L.rtg_splat_backward, L.rtg_splat_backward_render, L.rtg_splat_backward_finish):
         assert fn(None, 1, 16, *(nul * 6), *(nul * 4), 0, None, *(nul * 4), None, *(nul * 8), None) == -1
         assert b"view is NULL" in L.rtg_last_error()
