@@ -246,6 +246,31 @@ int rtg_map_adam_step(const RtgMapStep *step, void *stream);
 int rtg_map_activate(int32_t P, const float *scaling_raw, const float *rotation_raw, const float *opacity_raw,
                      float *scales_out, float *rotations_out, float *opacities_out, float *normal_out, void *stream);
 
+/* Mapping.history_merge (SLAM/multiprocess/mapper.py:212-250) with slerp of SLAM/utils.py:593-652: after an optimisation
+ * call, pull the raw parameters back towards their pre-optimisation values (`history_stat`, mapper.py:146-155):
+ *   w = max_weight * hist_confidence / (confidence + 1e-6)                                  per Gaussian,
+ *   _xyz          <- hist_xyz * w + (1 - w) * _xyz,
+ *   _features_dc, _features_rest, _scaling  <- hist * w[0] + (1 - w[0]) * current    (the reference indexes
+ *                    `history_weight[0]`: the FIRST Gaussian's weight for every row -- kept),
+ *   _rotation     <- slerp(hist_rotation, normalize(_rotation), 1 - w)   (linear where |dot| > 0.9995 or NaN).
+ * One launch instead of ~45 eager kernels; all updates in place. hist_rotation is get_rotation before the optimisation
+ * (normalised); rotation_raw is `_rotation` (16-byte aligned). features_dc / features_rest rows start every
+ * `*_stride` floats (3 / 45 for separate contiguous tensors, 48 for the two slices of one (P,16,3) block);
+ * hist arrays are contiguous. max_weight <= 0 or P == 0: nothing is done (mapper.py:213-214). */
+typedef struct RtgHistoryMerge {
+    int32_t P;
+    float max_weight;             /* history_merge_max_weight, configs/base.yaml:54 */
+    const float *hist_confidence, *confidence;          /* (P) */
+    const float *hist_xyz;      float *xyz;             /* (P,3) */
+    const float *hist_features_dc;   float *features_dc;    /* rows of 3 */
+    const float *hist_features_rest; float *features_rest;  /* rows of features_rest_width (45 for SH degree 3) */
+    const float *hist_scaling;  float *scaling;         /* (P,3) */
+    const float *hist_rotation; float *rotation_raw;    /* (P,4) */
+    int32_t features_dc_stride, features_rest_stride, features_rest_width;
+    int32_t _pad;
+} RtgHistoryMerge;
+int rtg_map_history_merge(const RtgHistoryMerge *merge, void *stream);
+
 /* ---- projective point-to-plane ICP ---------------------------------------------------------
  * Pyramid level: replaces nn.MaxPool2d(pool) (SLAM/icp.py:343-345,374) + compute_vertex_map
  * (SLAM/utils.py:65-75) + compute_normal_map (SLAM/utils.py:100-122). `depth`: (H,W) full

@@ -48,6 +48,15 @@ class RtgMapStep(C.Structure):
                 + [(n, C.c_void_p) for n in ("scales_out", "rotations_out", "opacities_out", "normal_out", "confidence")])
 
 
+class RtgHistoryMerge(C.Structure):
+    """include/rtg_splat_b200.h: RtgHistoryMerge (field order is the ABI)."""
+    _fields_ = ([("P", C.c_int32), ("max_weight", C.c_float)]
+                + [(n, C.c_void_p) for n in ("hist_confidence", "confidence", "hist_xyz", "xyz", "hist_features_dc", "features_dc",
+                                             "hist_features_rest", "features_rest", "hist_scaling", "scaling", "hist_rotation",
+                                             "rotation_raw")]
+                + [(n, C.c_int32) for n in ("features_dc_stride", "features_rest_stride", "features_rest_width", "_pad")])
+
+
 class RtgIcpLevel(C.Structure):
     _fields_ = [("vertex0", C.c_void_p), ("normal0", C.c_void_p), ("vertex1", C.c_void_p), ("normal1", C.c_void_p),
                 ("H", C.c_int32), ("W", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
@@ -75,6 +84,7 @@ SIGNATURES = {
     "rtg_adam_step": (C.c_int, [C.POINTER(RtgAdamGroup), _I32, _F, _F, _F, _I32, _VP]),
     "rtg_map_adam_step": (C.c_int, [C.POINTER(RtgMapStep), _VP]),
     "rtg_map_activate": (C.c_int, [_I32] + [_VP] * 8),
+    "rtg_map_history_merge": (C.c_int, [C.POINTER(RtgHistoryMerge), _VP]),
     "rtg_icp_workspace_bytes": (C.c_size_t, [_I32, _I32]),
     "rtg_icp_build_level": (C.c_int, [_VP, _I32, _I32, _I32, _F, _F, _F, _F, _VP, _VP, _VP, _VP]),
     "rtg_icp_solve_level": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _F, _F, _F, _F, _F, _F, _F, _I32, _VP, _VP, _VP, _VP]),

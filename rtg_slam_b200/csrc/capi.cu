@@ -15,6 +15,7 @@
 namespace rtg {
 int launch_adam(const RtgAdamGroup *groups, int n_groups, float beta1, float beta2, float eps, int step, cudaStream_t s);
 void launch_map_adam_step(const RtgMapStep &st, cudaStream_t s);
+void launch_history_merge(const RtgHistoryMerge &m, cudaStream_t s);
 void launch_map_activate(int P, const float *scaling_raw, const float *rotation_raw, const float *opacity_raw, float *scales_out,
                          float *rotations_out, float *opacities_out, float *normal_out, cudaStream_t s);
 size_t icp_ws_bytes();
@@ -458,6 +459,21 @@ int rtg_map_activate(int32_t P, const float *scaling_raw, const float *rotation_
     rtg::launch_map_activate(P, scaling_raw, rotation_raw, opacity_raw, scales_out, rotations_out, opacities_out, normal_out,
                              reinterpret_cast<cudaStream_t>(stream));
     return check_launch("rtg_map_activate");
+}
+
+int rtg_map_history_merge(const RtgHistoryMerge *m, void *stream) {
+    if (!m) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_history_merge: merge is NULL");
+    if (m->P < 0) return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_history_merge: P < 0");
+    if (m->P == 0 || !(m->max_weight > 0.f)) return RTG_OK;
+    if (!m->hist_confidence || !m->confidence || !m->hist_xyz || !m->xyz || !m->hist_features_dc || !m->features_dc ||
+        !m->hist_features_rest || !m->features_rest || !m->hist_scaling || !m->scaling || !m->hist_rotation || !m->rotation_raw)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_history_merge: NULL pointer");
+    if (m->features_rest_width < 0 || m->features_dc_stride < 3 || m->features_rest_stride < m->features_rest_width)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_history_merge: bad feature strides");
+    if ((((uintptr_t)m->hist_rotation) | ((uintptr_t)m->rotation_raw)) & 15)
+        return fail(RTG_ERR_INVALID_ARGUMENT, "rtg_map_history_merge: rotation tensors must be 16-byte aligned");
+    rtg::launch_history_merge(*m, reinterpret_cast<cudaStream_t>(stream));
+    return check_launch("rtg_map_history_merge");
 }
 
 size_t rtg_icp_workspace_bytes(int32_t H, int32_t W) {

@@ -241,6 +241,91 @@ __global__ void __launch_bounds__(256) map_activate_kernel(const int P, const fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Mapping.history_merge (SLAM/multiprocess/mapper.py:212-250): after an optimisation call the raw parameters are pulled
+// back towards their pre-optimisation values with the weight  w = max_weight * confidence_before / (confidence_now + 1e-6).
+// The reference evaluates it with ~45 eager kernels (slerp alone is ~30, SLAM/utils.py:593-652); here one launch: grid row
+// y = 0 merges _xyz (per-row weight) and the rotation (slerp with t = 1 - w), rows y = 1..3 the three arrays that the
+// reference merges with `history_weight[0]`, the weight of the FIRST Gaussian (mapper.py:229,234,239 -- kept as is).
+// Products and sums are the reference's separate fp32 operations (no contraction into FMAs).
+struct HistLerpSeg {
+    const float *hist;  // (P, width) contiguous
+    float *cur;         // row r at cur + r * stride
+    int width, stride;
+};
+
+struct HistMergeArgs {
+    RtgHistoryMerge m;
+    HistLerpSeg seg[3];
+};
+
+__device__ __forceinline__ float hist_weight(const HistMergeArgs &a, const int row) {
+    return __fdiv_rn(__fmul_rn(a.m.max_weight, __ldg(a.m.hist_confidence + row)), __fadd_rn(__ldg(a.m.confidence + row), 1e-6f));
+}
+
+// hist * w + (1 - w) * cur
+__device__ __forceinline__ float hist_mix(const float h, const float c, const float w) {
+    return __fadd_rn(__fmul_rn(h, w), __fmul_rn(__fsub_rn(1.0f, w), c));
+}
+
+// torch.lerp(start, end, weight) (ATen/native/Lerp.h)
+__device__ __forceinline__ float torch_lerp(const float start, const float end, const float w) {
+    const float diff = __fsub_rn(end, start);
+    return (fabsf(w) < 0.5f) ? fmaf(w, diff, start) : fmaf(-diff, __fsub_rn(1.0f, w), end);
+}
+
+__global__ void __launch_bounds__(256) history_merge_kernel(const HistMergeArgs a) {
+    const int P = a.m.P;
+    if (blockIdx.y == 0) {
+        const int row = blockIdx.x * blockDim.x + threadIdx.x;
+        if (row >= P) return;
+        const float w = hist_weight(a, row);
+        float *x = a.m.xyz + 3 * (size_t)row;
+        const float *hx = a.m.hist_xyz + 3 * (size_t)row;
+        const float x0 = hist_mix(__ldg(hx), x[0], w), x1 = hist_mix(__ldg(hx + 1), x[1], w), x2 = hist_mix(__ldg(hx + 2), x[2], w);
+        x[0] = x0; x[1] = x1; x[2] = x2;
+        // slerp(history rotation, normalize(_rotation), 1 - w)  (SLAM/utils.py:593-652; get_rotation = F.normalize)
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(a.m.hist_rotation) + row);
+        float4 *qp = reinterpret_cast<float4 *>(a.m.rotation_raw) + row;
+        float nn;
+        const float4 v1 = normalize4(*qp, nn);
+        const float t = __fsub_rn(1.0f, w);
+        const float n0 = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v0.x, v0.x), __fmul_rn(v0.y, v0.y)), __fmul_rn(v0.z, v0.z)), __fmul_rn(v0.w, v0.w)));
+        const float n1 = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v1.x, v1.x), __fmul_rn(v1.y, v1.y)), __fmul_rn(v1.z, v1.z)), __fmul_rn(v1.w, v1.w)));
+        const float dot = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__fdiv_rn(v0.x, n0), __fdiv_rn(v1.x, n1)), __fmul_rn(__fdiv_rn(v0.y, n0), __fdiv_rn(v1.y, n1))),
+                                              __fmul_rn(__fdiv_rn(v0.z, n0), __fdiv_rn(v1.z, n1))), __fmul_rn(__fdiv_rn(v0.w, n0), __fdiv_rn(v1.w, n1)));
+        float4 o;
+        if (isnan(dot) || fabsf(dot) > 0.9995f) {  // (nearly) collinear or a zero quaternion: linear
+            o = make_float4(torch_lerp(v0.x, v1.x, t), torch_lerp(v0.y, v1.y, t), torch_lerp(v0.z, v1.z, t), torch_lerp(v0.w, v1.w, t));
+        } else {
+            const float theta0 = acosf(dot), sin0 = sinf(theta0), theta_t = __fmul_rn(theta0, t);
+            const float s0 = __fdiv_rn(sinf(__fsub_rn(theta0, theta_t)), sin0), s1 = __fdiv_rn(sinf(theta_t), sin0);
+            o = make_float4(__fadd_rn(__fmul_rn(s0, v0.x), __fmul_rn(s1, v1.x)), __fadd_rn(__fmul_rn(s0, v0.y), __fmul_rn(s1, v1.y)),
+                            __fadd_rn(__fmul_rn(s0, v0.z), __fmul_rn(s1, v1.z)), __fadd_rn(__fmul_rn(s0, v0.w), __fmul_rn(s1, v1.w)));
+        }
+        *qp = o;
+        return;
+    }
+    const HistLerpSeg &g = a.seg[blockIdx.y - 1];
+    const float w0 = hist_weight(a, 0);  // history_weight[0]
+    const size_t n = (size_t)P * (size_t)g.width;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (size_t)g.width;
+        float *c = g.cur + r * (size_t)g.stride + (i - r * (size_t)g.width);
+        *c = hist_mix(__ldg(g.hist + i), *c, w0);
+    }
+}
+
+void launch_history_merge(const RtgHistoryMerge &m, cudaStream_t s) {
+    HistMergeArgs a;
+    a.m = m;
+    a.seg[0] = {m.hist_features_dc, m.features_dc, 3, m.features_dc_stride};
+    a.seg[1] = {m.hist_features_rest, m.features_rest, m.features_rest_width, m.features_rest_stride};
+    a.seg[2] = {m.hist_scaling, m.scaling, 3, 3};
+    ProfScope ps(K_ADAM, s);
+    history_merge_kernel<<<dim3((m.P + 255) / 256, 4), 256, 0, s>>>(a);
+}
+
 void launch_map_adam_step(const RtgMapStep &st, cudaStream_t s) {
     MapStepArgs a;
     a.s = st;

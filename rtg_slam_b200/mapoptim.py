@@ -25,7 +25,10 @@ nor read.
         with visible_rows_only():
             loss.backward()
         opt.step(radii=out["radii"])                                   # also zero_grad(set_to_none=True)
+    opt.history_merge(history_stat, self.history_merge_max_weight)     # replaces Mapping.history_merge, one kernel
     opt.write_back(pointcloud)                                         # replaces pointcloud.detach()
+
+`history_merge(...)` (module level) is the same kernel on the reference's own tensors.
 """
 from __future__ import annotations
 
@@ -34,13 +37,57 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import RtgMapStep, check
+from ._lib import RtgHistoryMerge, RtgMapStep, check
 
 GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")  # order of parametrize's list
 
 
 def _p(t):
     return None if t is None else t.data_ptr()
+
+
+def _merge_call(history_stat, confidence, xyz, dc, dc_stride, rest, rest_stride, rest_width, scaling, rotation_raw, max_weight,
+                device):
+    P = xyz.shape[0]
+
+    def hist(key, numel):
+        t = history_stat[key]
+        if not t.is_cuda or t.device != device or t.dtype != torch.float32 or t.numel() != numel:
+            raise TypeError(f"history_merge: history_stat['{key}'] must be a float32 tensor with {numel} elements on {device}")
+        return t.contiguous()
+    keep = [hist("confidence", P), hist("xyz", 3 * P), hist("features_dc", 3 * P), hist("features_rest", rest_width * P),
+            hist("scaling", 3 * P), hist("rotation", 4 * P)]
+    m = RtgHistoryMerge()
+    m.P, m.max_weight = P, float(max_weight)
+    m.hist_confidence, m.hist_xyz, m.hist_features_dc, m.hist_features_rest, m.hist_scaling, m.hist_rotation = (_p(t) for t in keep)
+    m.confidence, m.xyz, m.features_dc, m.features_rest, m.scaling, m.rotation_raw = (_p(t) for t in (confidence, xyz, dc, rest, scaling,
+                                                                                                        rotation_raw))
+    m.features_dc_stride, m.features_rest_stride, m.features_rest_width = int(dc_stride), int(rest_stride), int(rest_width)
+    with torch.cuda.device(device):
+        check(_lib.lib().rtg_map_history_merge(C.byref(m), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+              "rtg_map_history_merge")
+
+
+@torch.no_grad()
+def history_merge(history_stat, confidence, xyz, features_dc, features_rest, scaling, rotation, max_weight=0.5):
+    """`Mapping.history_merge` (SLAM/multiprocess/mapper.py:212-250) in one kernel, IN PLACE on the raw parameter tensors of
+    a GaussianPointCloud: `history_merge(history_stat, pc._confidence, pc._xyz, pc._features_dc, pc._features_rest, pc._scaling,
+    pc._rotation, max_weight)`. `history_stat` is the dict local_optimize builds before the loop (mapper.py:146-155; keys
+    used: confidence, xyz, features_dc, features_rest, scaling, rotation = get_rotation). Like the reference, the features
+    and the scaling are merged with the first Gaussian's weight (`history_weight[0]`) and a non-positive `max_weight`
+    does nothing. The tensors must be contiguous float32 CUDA tensors (they are updated through their storage)."""
+    if max_weight <= 0:
+        return
+    dev = xyz.device
+    P = xyz.shape[0]
+    if P == 0:
+        return
+    width = features_rest.numel() // P
+    for name, t, numel in (("confidence", confidence, P), ("xyz", xyz, 3 * P), ("features_dc", features_dc, 3 * P),
+                           ("features_rest", features_rest, width * P), ("scaling", scaling, 3 * P), ("rotation", rotation, 4 * P)):
+        if not t.is_cuda or t.device != dev or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != numel:
+            raise TypeError(f"history_merge: {name} must be a contiguous float32 tensor with {numel} elements on {dev}")
+    _merge_call(history_stat, confidence, xyz, features_dc, 3, features_rest, width, width, scaling, rotation, max_weight, dev)
 
 
 class MapOptimizer:
@@ -119,6 +166,30 @@ class MapOptimizer:
         pc._scaling = self.scaling_raw
         pc._rotation = self.rotation_raw
         return pc
+
+    # ------------------------------------------------------------------ history merge (mapper.py:146-155,210-250)
+    def history_snapshot(self):
+        """The `history_stat` dict `Mapping.local_optimize` builds before its loop (mapper.py:146-155) from the optimiser's
+        current state: clones of the raw parameters, the activated rotation and the confidence."""
+        if self.confidence is None:
+            raise RuntimeError("MapOptimizer.history_snapshot: no confidence tensor was given to the optimiser")
+        return {"opacity": self.opacity_raw.clone(), "confidence": self.confidence.detach().clone().view(-1, 1),
+                "xyz": self.xyz.detach().clone(), "features_dc": self.features_dc.clone(), "features_rest": self.features_rest.clone(),
+                "scaling": self.scaling_raw.clone(), "rotation": self.rotations.detach().clone(), "rotation_raw": self.rotation_raw.clone()}
+
+    @torch.no_grad()
+    def history_merge(self, history_stat, max_weight=0.5):
+        """`Mapping.history_merge` (mapper.py:212-250) on the optimiser's own tensors, in place, followed by the activation
+        forward so that `gaussian_data()` is consistent again. Call it after the loop, before `write_back`."""
+        if max_weight <= 0 or self.P == 0:
+            return
+        if self.confidence is None:
+            raise RuntimeError("MapOptimizer.history_merge: no confidence tensor was given to the optimiser")
+        sh = self.shs.detach()
+        _merge_call(history_stat, self.confidence, self.xyz.detach(), sh, 48, sh.view(-1)[3:], 48, 45, self.scaling_raw,
+                    self.rotation_raw, max_weight, self.device)
+        check(_lib.lib().rtg_map_activate(self.P, _p(self.scaling_raw), _p(self.rotation_raw), _p(self.opacity_raw), _p(self.scales),
+                                          _p(self.rotations), _p(self.opacity), _p(self.normal), self._stream()), "rtg_map_activate")
 
     # ------------------------------------------------------------------ views
     @property

@@ -182,3 +182,56 @@ def frameprep_inputs(name):
     depth[: cam.height // 6, : cam.width // 5] = 0          # a larger missing region
     K = [[cam.fx, 0.0, cam.cx], [0.0, cam.fy, cam.cy], [0.0, 0.0, 1.0]]
     return np.ascontiguousarray(depth, dtype=np.float32), K
+
+
+# ----------------------------------------------------------------------------- Mapping.history_merge (mapper.py:212-250)
+HISTORY_MERGE_SIZES = {"window": 777, "one": 1}
+
+
+def history_merge_inputs(name):
+    """Seeded (history_stat, current state) pair as local_optimize leaves them: the optimisation moved every raw parameter a
+    little; a few quaternions moved a lot (the spherical branch of slerp), a few flipped sign (dot < 0), three history
+    quaternions are zero (NaN dot -> linear branch). Rows whose |dot| lies within 2e-5 of the 0.9995 branch threshold are
+    regenerated away from it (the branch must not depend on the last bit of a norm)."""
+    P = HISTORY_MERGE_SIZES[name]
+    rng = np.random.default_rng(1000 + P)
+    f = np.float32
+    hist_conf = rng.integers(0, 40, size=(P, 1)).astype(f)
+    conf = hist_conf + rng.integers(0, 51, size=(P, 1)).astype(f)
+    if P > 3:
+        conf[1], hist_conf[1] = 0, 0                       # a Gaussian that never received a gradient: weight 0 / 1e-6 = 0
+    hist = {"confidence": hist_conf, "xyz": rng.normal(size=(P, 3)).astype(f), "features_dc": rng.normal(size=(P, 1, 3)).astype(f),
+            "features_rest": (0.1 * rng.normal(size=(P, 15, 3))).astype(f), "scaling": (rng.normal(size=(P, 3)) - 3).astype(f)}
+    q = rng.normal(size=(P, 4))
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    hist["rotation"] = q.astype(f)
+    cur = {"confidence": conf}
+    for k, sig in (("xyz", 0.01), ("features_dc", 0.05), ("features_rest", 0.02), ("scaling", 0.1)):
+        cur[k] = (hist[k] + sig * rng.normal(size=hist[k].shape)).astype(f)
+    noise = 0.01 * rng.normal(size=(P, 4))
+    big = rng.uniform(size=P) < 0.2
+    noise[big] = 0.6 * rng.normal(size=(int(big.sum()), 4))
+    raw = (q + noise) * rng.uniform(0.5, 2.0, size=(P, 1))    # the raw rotation is not normalised
+    flip = rng.uniform(size=P) < 0.1
+    raw[flip] *= -1
+    cur["rotation_raw"] = raw.astype(f)
+    if P > 10:
+        hist["rotation"][5:8] = 0
+    rn = cur["rotation_raw"].astype(np.float64)
+    rn /= np.linalg.norm(rn, axis=-1, keepdims=True)
+    hn = hist["rotation"].astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        dot = np.abs((hn / np.linalg.norm(hn, axis=-1, keepdims=True) * rn).sum(-1))
+    near = np.abs(dot - 0.9995) < 2e-5
+    cur["rotation_raw"][near] = (hist["rotation"][near] * 1.5).astype(f)   # collinear: far inside the linear branch
+    return hist, cur
+
+
+def slerp_tolerance(dot, base=4e-7):
+    """Per-row bound on |slerp - reference slerp| for fp32 evaluations that differ in libm / summation order: `base` on the
+    linear branch, base / sin(theta_0) on the spherical one (s0, s1 = sin(.) / sin(theta_0), SLAM/utils.py:646-648)."""
+    with np.errstate(invalid="ignore"):
+        d = np.nan_to_num(np.abs(dot.astype(np.float64)), nan=1.0)
+        lin = d > 0.9995
+        s = np.sqrt(np.maximum(1.0 - np.minimum(d, 1.0) ** 2, 1e-6))
+    return np.where(lin, base, base / s + base)

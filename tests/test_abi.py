@@ -30,6 +30,7 @@ def test_view_struct_layout_matches_header():
     assert C.sizeof(_lib.RtgSplatView) == 14 * 4 + 4 * 8
     assert _lib.RtgSplatView.viewmatrix.offset == 56
     assert C.sizeof(_lib.RtgAdamGroup) == 48
+    assert C.sizeof(_lib.RtgHistoryMerge) == 2 * 4 + 12 * 8 + 4 * 4 and _lib.RtgHistoryMerge.features_dc_stride.offset == 104
 
 
 def test_workspace_bytes_is_host_only_and_monotone():
@@ -72,6 +73,14 @@ def test_side_entry_points_validate_before_touching_cuda():
     assert b"rtg_frame_preprocess" in L.rtg_last_error()
     assert L.rtg_loss_l1(*(nul * 6), 16, 16, 0, 0.8, 1.0, 0.1, *(nul * 5)) == -1
     assert L.rtg_normal_map(None, None, 16, 16, None, None) == -1
+    assert L.rtg_map_history_merge(None, None) == -1 and b"merge is NULL" in L.rtg_last_error()
+    hm = _lib.RtgHistoryMerge()
+    hm.P, hm.max_weight = 0, 0.5
+    assert L.rtg_map_history_merge(C.byref(hm), None) == 0          # empty map: nothing to do
+    hm.P = 4
+    assert L.rtg_map_history_merge(C.byref(hm), None) == -1 and b"NULL pointer" in L.rtg_last_error()
+    hm.max_weight = 0.0
+    assert L.rtg_map_history_merge(C.byref(hm), None) == 0          # disabled (mapper.py:213-214)
     assert L.rtg_ssim_loss(None, None, 3, 16, 16, None, None, None, None) == -1 and b"rtg_ssim_loss" in L.rtg_last_error()
     # partial sums (one double per 16x16 tile and channel, 256-byte aligned) + three derivative maps
     assert L.rtg_ssim_workspace_bytes(3, 680, 1200) == ((3 * 43 * 75 * 8 + 255) // 256) * 256 + 3 * 3 * 680 * 1200 * 4

@@ -240,3 +240,85 @@ def test_map_optimizer_loop_matches_eager_flow_through_the_rasterizer(cuda_devic
         off = float((diff > 1e-5 * scale).float().mean())
         assert off < 5e-3, (k, off)
         assert float(diff.max()) <= 2.0 * max(lrs.values()) * iters + 1e-6, k
+
+
+# ----------------------------------------------------------------------------- Mapping.history_merge (mapper.py:212-250)
+def _close_fp32(a, b, ulps=2):
+    return np.all(np.abs(a.astype(np.float64) - b.astype(np.float64)) <= ulps * 1.2e-7 * np.maximum(1.0, np.abs(b)))
+
+
+@pytest.mark.parametrize("name", sorted(helpers.HISTORY_MERGE_SIZES))
+@pytest.mark.parametrize("max_weight", [0.5, 0.9])
+def test_history_merge_matches_reference_golden(cuda_device, name, max_weight):
+    """mapoptim.history_merge (one kernel, in place) against the golden outputs of the reference's own expressions with its
+    unmodified slerp (tests/golden/history_merge.npz) and against the numpy oracle. The lerps are the same fp32 operations in
+    the same order; the rotation is bounded per row by the conditioning of slerp (helpers.slerp_tolerance)."""
+    import os
+    from oracle import mapmerge_oracle as mm
+    from rtg_slam_b200.mapoptim import history_merge
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "history_merge.npz"))
+    hist, cur = helpers.history_merge_inputs(name)
+    dev = cuda_device
+    h = {k: torch.from_numpy(v).to(dev) for k, v in hist.items()}
+    c = {k: torch.from_numpy(v.copy()).to(dev) for k, v in cur.items()}
+    history_merge(h, c["confidence"], c["xyz"], c["features_dc"], c["features_rest"], c["scaling"], c["rotation_raw"], max_weight)
+    want, dot = mm.history_merge(hist, cur, max_weight)
+    for k, ck in (("xyz", "xyz"), ("features_dc", "features_dc"), ("features_rest", "features_rest"), ("scaling", "scaling")):
+        got = c[ck].cpu().numpy()
+        assert _close_fp32(got, gold[f"{name}_{max_weight}_{k}"]), k
+        assert _close_fp32(got, want[k]), k
+    got = c["rotation_raw"].cpu().numpy()
+    tol = 2 * helpers.slerp_tolerance(dot)
+    assert np.isfinite(got).all()
+    assert np.all(np.abs(got - gold[f"{name}_{max_weight}_rotation"]).max(-1) <= tol)
+    assert torch.equal(c["confidence"].cpu(), torch.from_numpy(cur["confidence"]))   # inputs other than the five are untouched
+    # a non-positive weight leaves everything as it is (mapper.py:213-214)
+    before = c["xyz"].clone()
+    history_merge(h, c["confidence"], c["xyz"], c["features_dc"], c["features_rest"], c["scaling"], c["rotation_raw"], 0.0)
+    assert torch.equal(before, c["xyz"])
+
+
+def test_map_optimizer_history_merge_on_the_sh_block(cuda_device):
+    """MapOptimizer.history_snapshot / history_merge: the same kernel on the optimiser's own layout (features_dc / features_rest
+    are the two slices of one (P,16,3) block, row stride 48) and the activation forward afterwards."""
+    from oracle import mapmerge_oracle as mm
+    from rtg_slam_b200.mapoptim import MapOptimizer
+    dev = cuda_device
+    hist, cur = helpers.history_merge_inputs("window")
+    P = hist["xyz"].shape[0]
+    t = lambda a: torch.from_numpy(a.copy()).to(dev)
+    opacity = torch.randn(P, 1, device=dev)
+    conf = t(hist["confidence"]).view(-1).contiguous()
+    # the optimiser starts from the history state ...
+    raw_rot0 = t(hist["rotation"]) * 1.7          # raw quaternion whose normalisation is the history rotation
+    raw_rot0[5:8] = 0                             # zero quaternions stay zero under F.normalize
+    opt = MapOptimizer(t(hist["xyz"]), t(hist["features_dc"]), t(hist["features_rest"]), opacity, t(hist["scaling"]), raw_rot0,
+                       [1e-3] * 6, confidence=conf)
+    snap = opt.history_snapshot()
+    assert set(snap) == {"opacity", "confidence", "xyz", "features_dc", "features_rest", "scaling", "rotation", "rotation_raw"}  # mapper.py:146-155
+    assert snap["confidence"].shape == (P, 1) and snap["features_rest"].shape == (P, 15, 3) and snap["features_rest"].is_contiguous()
+    # ... and "optimises" to the current state of the fixture
+    with torch.no_grad():
+        opt.xyz.copy_(t(cur["xyz"]))
+        opt.shs[:, :1].copy_(t(cur["features_dc"]))
+        opt.shs[:, 1:].copy_(t(cur["features_rest"]))
+        opt.scaling_raw.copy_(t(cur["scaling"]))
+        opt.rotation_raw.copy_(t(cur["rotation_raw"]))
+        conf.copy_(t(cur["confidence"]).view(-1))
+    opt.history_merge(snap, 0.5)
+    hist_used = dict(hist)
+    hist_used["rotation"] = snap["rotation"].cpu().numpy()    # normalize(1.7 q): equal to the fixture's up to rounding
+    want, dot = mm.history_merge(hist_used, cur, 0.5)
+    assert _close_fp32(opt.xyz.detach().cpu().numpy(), want["xyz"])
+    assert _close_fp32(opt.features_dc.cpu().numpy(), want["features_dc"])
+    assert _close_fp32(opt.features_rest.cpu().numpy(), want["features_rest"])
+    assert _close_fp32(opt.scaling_raw.cpu().numpy(), want["scaling"])
+    assert np.all(np.abs(opt.rotation_raw.cpu().numpy() - want["rotation"]).max(-1) <= 2 * helpers.slerp_tolerance(dot))
+    assert torch.equal(opt.opacity_raw, opacity)                                      # _opacity is not merged
+    # activated tensors follow the merged raw parameters
+    d = opt.gaussian_data()
+    assert torch.allclose(d["rotations"], F.normalize(opt.rotation_raw), atol=1e-6)
+    assert torch.allclose(d["scales"], torch.exp(opt.scaling_raw), rtol=1e-6)
+    with pytest.raises(RuntimeError):
+        MapOptimizer(t(hist["xyz"]), t(hist["features_dc"]), t(hist["features_rest"]), opacity, t(hist["scaling"]), raw_rot0,
+                     [1e-3] * 6).history_snapshot()
