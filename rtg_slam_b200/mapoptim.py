@@ -29,6 +29,11 @@ nor read.
     opt.write_back(pointcloud)                                         # replaces pointcloud.detach()
 
 `history_merge(...)` (module level) is the same kernel on the reference's own tensors.
+
+`frozen=` appends Gaussians that are rendered but not optimised -- the reference's `global_params` is
+`cat(unstable (requires grad), stable (detached))`, rebuilt from both clouds' activation properties in EVERY iteration
+(mapper.py:1034-1108: ~10 activation kernels over the stable map + 8 `torch.cat`). Here the stable rows are copied once
+behind the optimised rows of the same buffers; `step()` only ever touches the first P rows.
 """
 from __future__ import annotations
 
@@ -92,11 +97,13 @@ def history_merge(history_stat, confidence, xyz, features_dc, features_rest, sca
 
 class MapOptimizer:
     def __init__(self, xyz, features_dc, features_rest, opacity, scaling, rotation, lrs, betas=(0.9, 0.999), eps=1e-15,
-                 confidence=None, attach_weight=1000.0):
+                 confidence=None, attach_weight=1000.0, frozen=None):
         """Raw parameter tensors as GaussianPointCloud holds them: `_xyz (P,3)`, `_features_dc (P,1,3)`,
         `_features_rest (P,15,3)`, `_opacity (P,1)`, `_scaling (P,3)`, `_rotation (P,4)` (values are copied).
         `lrs`: dict by GROUPS (or a 6-sequence in that order). `confidence`: optional (P,) / (P,1) float tensor, updated
-        in place by step()."""
+        in place by step(). `frozen`: optional dict of ACTIVATED tensors of S Gaussians that are rendered but not
+        optimised (`Mapping.stable_params`, mapper.py:997-1022: xyz (S,3), opacity (S,1), scales (S,3), rotations (S,4),
+        shs (S,16,3), normal (S,3)); they become rows P..P+S-1 of the tensors of `gaussian_data()`."""
         dev = xyz.device
         if dev.type != "cuda":
             raise TypeError("MapOptimizer: parameters must be CUDA tensors (there is no CPU path)")
@@ -111,30 +118,46 @@ class MapOptimizer:
         if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0) or eps < 0:
             raise ValueError("MapOptimizer: invalid betas / eps")
         self.device, self.P = dev, P
+        S = 0
+        if frozen is not None:
+            S = int(frozen["xyz"].shape[0])
+            for name, shape in (("xyz", (S, 3)), ("opacity", (S, 1)), ("scales", (S, 3)), ("rotations", (S, 4)), ("shs", (S, 16, 3)),
+                                ("normal", (S, 3))):
+                t = frozen[name]
+                if t.dtype != torch.float32 or t.device != dev or tuple(t.shape) != shape:
+                    raise TypeError(f"MapOptimizer: frozen['{name}'] must be float32 {shape} on {dev}")
+        self.S = S  # frozen rows behind the P optimised ones
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
         self.lrs = dict(zip(GROUPS, lrs)) if not isinstance(lrs, dict) else {k: float(lrs[k]) for k in GROUPS}
         self.attach_weight = float(attach_weight)
         self.step_count = 0
         with torch.no_grad():
             # rasterizer inputs that are raw parameters themselves
-            self.xyz = xyz.detach().clone().contiguous().requires_grad_(True)
-            self.shs = torch.cat([features_dc.detach(), features_rest.detach()], dim=1).contiguous().requires_grad_(True)  # once
+            tail = lambda key: [frozen[key].detach()] if S else []
+            self.xyz = torch.cat([xyz.detach()] + tail("xyz"), dim=0).contiguous().requires_grad_(True)
+            self.shs = torch.cat([torch.cat([features_dc.detach(), features_rest.detach()], dim=1)] + tail("shs"),
+                                 dim=0).contiguous().requires_grad_(True)  # once
             # raw parameters behind an activation
             self.opacity_raw = opacity.detach().clone().contiguous()
             self.scaling_raw = scaling.detach().clone().contiguous()
             self.rotation_raw = rotation.detach().clone().contiguous()
             # activated leaves, rewritten by every step
-            self.opacity = torch.empty_like(self.opacity_raw)
-            self.scales = torch.empty_like(self.scaling_raw)
-            self.rotations = torch.empty_like(self.rotation_raw)
-            self.normal = torch.empty((P, 3), dtype=torch.float32, device=dev)
+            self.opacity = torch.empty((P + S, 1), dtype=torch.float32, device=dev)
+            self.scales = torch.empty((P + S, 3), dtype=torch.float32, device=dev)
+            self.rotations = torch.empty((P + S, 4), dtype=torch.float32, device=dev)
+            self.normal = torch.empty((P + S, 3), dtype=torch.float32, device=dev)
+            if S:
+                self.opacity[P:].copy_(frozen["opacity"])
+                self.scales[P:].copy_(frozen["scales"])
+                self.rotations[P:].copy_(frozen["rotations"])
+                self.normal[P:].copy_(frozen["normal"])
             check(_lib.lib().rtg_map_activate(P, _p(self.scaling_raw), _p(self.rotation_raw), _p(self.opacity_raw), _p(self.scales),
                                               _p(self.rotations), _p(self.opacity), _p(self.normal), self._stream()), "rtg_map_activate")
         for t in (self.opacity, self.scales, self.rotations):
             t.requires_grad_(True)
         self.state = {k: (torch.zeros_like(t), torch.zeros_like(t)) for k, t in
-                      (("xyz", self.xyz), ("sh", self.shs), ("opacity", self.opacity_raw), ("scaling", self.scaling_raw),
-                       ("rotation", self.rotation_raw))}
+                      (("xyz", self.xyz.detach()[:P]), ("sh", self.shs.detach()[:P]), ("opacity", self.opacity_raw),
+                       ("scaling", self.scaling_raw), ("rotation", self.rotation_raw))}
         if confidence is not None and (confidence.dtype != torch.float32 or confidence.numel() != P or not confidence.is_contiguous()
                                        or confidence.device != dev):
             raise TypeError("MapOptimizer: confidence must be a contiguous float32 tensor with one element per Gaussian")
@@ -159,7 +182,7 @@ class MapOptimizer:
     def write_back(self, pc):
         """The optimised raw parameters into a GaussianPointCloud, detached (what `pointcloud.detach()` leaves behind,
         gaussian_pointcloud.py:306-313). `_features_dc` / `_features_rest` become views of one (P,16,3) block."""
-        pc._xyz = self.xyz.detach()
+        pc._xyz = self.xyz.detach()[:self.P]
         pc._features_dc = self.features_dc
         pc._features_rest = self.features_rest
         pc._opacity = self.opacity_raw
@@ -174,8 +197,9 @@ class MapOptimizer:
         if self.confidence is None:
             raise RuntimeError("MapOptimizer.history_snapshot: no confidence tensor was given to the optimiser")
         return {"opacity": self.opacity_raw.clone(), "confidence": self.confidence.detach().clone().view(-1, 1),
-                "xyz": self.xyz.detach().clone(), "features_dc": self.features_dc.clone(), "features_rest": self.features_rest.clone(),
-                "scaling": self.scaling_raw.clone(), "rotation": self.rotations.detach().clone(), "rotation_raw": self.rotation_raw.clone()}
+                "xyz": self.xyz.detach()[:self.P].clone(), "features_dc": self.features_dc.clone(),
+                "features_rest": self.features_rest.clone(), "scaling": self.scaling_raw.clone(),
+                "rotation": self.rotations.detach()[:self.P].clone(), "rotation_raw": self.rotation_raw.clone()}
 
     @torch.no_grad()
     def history_merge(self, history_stat, max_weight=0.5):
@@ -185,8 +209,8 @@ class MapOptimizer:
             return
         if self.confidence is None:
             raise RuntimeError("MapOptimizer.history_merge: no confidence tensor was given to the optimiser")
-        sh = self.shs.detach()
-        _merge_call(history_stat, self.confidence, self.xyz.detach(), sh, 48, sh.view(-1)[3:], 48, 45, self.scaling_raw,
+        sh = self.shs.detach()[:self.P]
+        _merge_call(history_stat, self.confidence, self.xyz.detach()[:self.P], sh, 48, sh.view(-1)[3:], 48, 45, self.scaling_raw,
                     self.rotation_raw, max_weight, self.device)
         check(_lib.lib().rtg_map_activate(self.P, _p(self.scaling_raw), _p(self.rotation_raw), _p(self.opacity_raw), _p(self.scales),
                                           _p(self.rotations), _p(self.opacity), _p(self.normal), self._stream()), "rtg_map_activate")
@@ -194,15 +218,16 @@ class MapOptimizer:
     # ------------------------------------------------------------------ views
     @property
     def features_dc(self):
-        return self.shs.detach()[:, :1]
+        return self.shs.detach()[:self.P, :1]
 
     @property
     def features_rest(self):
-        return self.shs.detach()[:, 1:]
+        return self.shs.detach()[:self.P, 1:]
 
     def gaussian_data(self):
         """The dict `Renderer.render` takes (SLAM/render.py:93-98; what Mapping.get_render_output builds from the
-        pointcloud's get_* properties). The tensors are autograd leaves: backward leaves their `.grad` for step()."""
+        pointcloud's get_* properties; with `frozen`, the reference's `global_params`: optimised rows first, frozen rows
+        behind them). The tensors are autograd leaves: backward leaves their `.grad` for step()."""
         return {"xyz": self.xyz, "opacity": self.opacity, "scales": self.scales, "rotations": self.rotations, "shs": self.shs,
                 "normal": self.normal}
 
@@ -232,7 +257,7 @@ class MapOptimizer:
         def l2(a, b):
             return ((a[m] - b[m]) ** 2).mean()
         with torch.no_grad():
-            return self.attach_weight * (l2(self.scaling_raw, self._attach["scaling0"]) + l2(self.xyz, self._attach["xyz0"])
+            return self.attach_weight * (l2(self.scaling_raw, self._attach["scaling0"]) + l2(self.xyz.detach()[:self.P], self._attach["xyz0"])
                                          + l2(self.rotation_raw, self._attach["rotation0"]))
 
     # ------------------------------------------------------------------ the step
@@ -285,9 +310,9 @@ class MapOptimizer:
             if g.dtype != torch.float32 or g.device != self.device:
                 raise TypeError(f"MapOptimizer.step: gradient of '{name}' must be float32 on {self.device}")
             grads[name] = g if g.is_contiguous() else g.contiguous()
-        if radii is not None and (radii.dtype != torch.int32 or radii.numel() != self.P or radii.device != self.device
+        if radii is not None and (radii.dtype != torch.int32 or radii.numel() != self.P + self.S or radii.device != self.device
                                   or not radii.is_contiguous()):
-            raise TypeError("MapOptimizer.step: radii must be the rasterizer's contiguous int32 (P,) output")
+            raise TypeError("MapOptimizer.step: radii must be the rasterizer's contiguous int32 output (one entry per rendered Gaussian)")
         self.step_count += 1
         st = self._step_struct()
         st.step = self.step_count

@@ -322,3 +322,72 @@ def test_map_optimizer_history_merge_on_the_sh_block(cuda_device):
     with pytest.raises(RuntimeError):
         MapOptimizer(t(hist["xyz"]), t(hist["features_dc"]), t(hist["features_rest"]), opacity, t(hist["scaling"]), raw_rot0,
                      [1e-3] * 6).history_snapshot()
+
+
+def test_map_optimizer_with_frozen_stable_rows(cuda_device):
+    """`frozen=`: the reference renders `global_params = cat(unstable, stable.detach())` (mapper.py:1034-1108) and only the
+    unstable cloud is optimised. Here the stable rows sit behind the optimised rows of the same buffers; the fused step must
+    move exactly the first P rows like torch activations + torch.optim.Adam on the unstable parameters, leave the frozen
+    rows bit-identical, and history_snapshot / history_merge / write_back must see P rows."""
+    from rtg_slam_b200.mapoptim import MapOptimizer
+    dev = cuda_device
+    P, S, iters = 3001, 1777, 6
+    raw = _raw_map(P, dev, seed=11)
+    st = _raw_map(S, dev, seed=12)
+    frozen = dict(xyz=st["xyz"], opacity=torch.sigmoid(st["opacity"]), scales=torch.exp(st["scaling"]), rotations=F.normalize(st["rotation"]),
+                  shs=torch.cat([st["features_dc"], st["features_rest"]], 1).contiguous(), normal=_get_normal(st["scaling"], st["rotation"]))
+    torch.manual_seed(5)
+    vis = torch.rand(P + S, device=dev) < 0.5
+    shapes = dict(xyz=(P + S, 3), shs=(P + S, 16, 3), opacity=(P + S, 1), scales=(P + S, 3), rotations=(P + S, 4))
+    W = {k: torch.randn(s, device=dev) * vis.view(-1, *([1] * (len(s) - 1))).float() for k, s in shapes.items()}
+
+    def image_loss(d):
+        return sum((W[k] * (d[k] ** 2 + d[k])).sum() for k in W)
+
+    # ---- reference flow: parameters of the unstable cloud only, the stable activations are concatenated every iteration
+    p = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+    groups = [{"params": [p[k]], "lr": LRS[g]} for k, g in (("xyz", "xyz"), ("features_dc", "f_dc"), ("features_rest", "f_rest"),
+                                                          ("opacity", "opacity"), ("scaling", "scaling"), ("rotation", "rotation"))]
+    ref_opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+    for _ in range(iters):
+        un = dict(xyz=p["xyz"], shs=torch.cat((p["features_dc"], p["features_rest"]), dim=1), opacity=torch.sigmoid(p["opacity"]),
+                  scales=torch.exp(p["scaling"]), rotations=F.normalize(p["rotation"]))
+        image_loss({k: torch.cat([un[k], frozen[k].detach()]) for k in un}).backward()
+        ref_opt.step()
+        ref_opt.zero_grad(set_to_none=True)
+
+    # ---- fused flow
+    conf = torch.zeros(P, device=dev)
+    opt = MapOptimizer(raw["xyz"], raw["features_dc"], raw["features_rest"], raw["opacity"], raw["scaling"], raw["rotation"], LRS,
+                       confidence=conf, frozen=frozen)
+    d0 = opt.gaussian_data()
+    assert all(d0[k].shape[0] == P + S for k in ("xyz", "opacity", "scales", "rotations", "shs", "normal"))
+    snap = opt.history_snapshot()
+    assert snap["xyz"].shape == (P, 3) and snap["rotation"].shape == (P, 4) and snap["features_rest"].shape == (P, 15, 3)
+    radii = vis.to(torch.int32) * 3
+    for _ in range(iters):
+        image_loss({k: opt.gaussian_data()[k] for k in W}).backward()
+        for t in (opt.xyz, opt.shs, opt.opacity, opt.scales, opt.rotations):
+            t.grad[~vis] = float("nan")        # what rtg_splat_backward_visible leaves in culled rows
+        opt.step(radii=radii)
+
+    def rel(a, b):
+        return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12)
+    d = opt.gaussian_data()
+    assert rel(d["xyz"].detach()[:P], p["xyz"].detach()) < 1e-5 and rel(opt.features_rest, p["features_rest"].detach()) < 1e-5
+    assert rel(opt.scaling_raw, p["scaling"].detach()) < 1e-5 and rel(opt.rotation_raw, p["rotation"].detach()) < 1e-5
+    assert rel(d["scales"].detach()[:P], torch.exp(p["scaling"].detach())) < 1e-5
+    assert float((p["xyz"].detach() - raw["xyz"]).abs().max()) > 0
+    for k in ("xyz", "opacity", "scales", "rotations", "shs", "normal"):        # the frozen rows never move
+        assert torch.equal(d[k].detach()[P:], frozen[k]), k
+    assert float(conf.max()) == iters and conf.numel() == P
+    # history merge and write-back act on the optimised rows only
+    opt.history_merge(snap, 0.5)
+    for k in ("xyz", "shs", "rotations"):
+        assert torch.equal(opt.gaussian_data()[k].detach()[P:], frozen[k]), k
+    pc = opt.write_back(type("PC", (), {})())
+    assert pc._xyz.shape == (P, 3) and pc._features_dc.shape == (P, 1, 3) and pc._features_rest.shape == (P, 15, 3)
+    assert pc._rotation.shape == (P, 4) and pc._opacity.shape == (P, 1)
+    with pytest.raises(TypeError):
+        MapOptimizer(raw["xyz"], raw["features_dc"], raw["features_rest"], raw["opacity"], raw["scaling"], raw["rotation"], LRS,
+                     frozen=dict(frozen, shs=frozen["shs"][:, :4]))
