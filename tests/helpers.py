@@ -235,3 +235,25 @@ def slerp_tolerance(dot, base=4e-7):
         lin = d > 0.9995
         s = np.sqrt(np.maximum(1.0 - np.minimum(d, 1.0) ** 2, 1e-6))
     return np.where(lin, base, base / s + base)
+
+
+# ----------------------------------------------------------------------------- SSIM term (utils/loss_utils.py:40-100)
+SSIM_CASES = {"ragged": (3, 37, 53), "tile": (1, 16, 16), "strip": (2, 5, 40), "smooth": (3, 48, 80)}
+
+
+def ssim_inputs(name):
+    """Seeded (render, frame) pair, float32 (C,H,W) in [0,1]: noise whose upper half is a perturbed copy (high SSIM), or --
+    'smooth' -- low-frequency images with a black block each (sigma^2 next to C2, the ill-conditioned regime)."""
+    C, H, W = SSIM_CASES[name]
+    rng = np.random.default_rng(7000 + H * W)
+    if name == "smooth":
+        yy, xx = np.meshgrid(np.linspace(0, 1, H), np.linspace(0, 1, W), indexing="ij")
+        a = np.stack([0.5 + 0.4 * np.sin(6 * xx + c) * np.cos(4 * yy) for c in range(C)])
+        b = np.clip(a + 0.01 * rng.normal(size=a.shape), 0, 1)
+        a[:, : H // 4, : W // 3] = 0
+        b[:, : H // 5, : W // 4] = 0
+    else:
+        a = rng.uniform(size=(C, H, W))
+        b = rng.uniform(size=(C, H, W))
+        b[:, : H // 2] = np.clip(a[:, : H // 2] + 0.02 * rng.normal(size=(C, H // 2, W)), 0, 1)
+    return a.astype(np.float32), b.astype(np.float32)
