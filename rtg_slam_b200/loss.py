@@ -152,6 +152,8 @@ class _FusedSsim(torch.autograd.Function):
         ws = _SSIM_WS.get(idx)
         if ws is None or ws.numel() < need:
             ws = _SSIM_WS[idx] = torch.empty(need, dtype=torch.uint8, device=dev)
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("ssim_loss: the gradient w.r.t. img2 (the measured frame) is not implemented; detach it")
         want_grad = ctx.needs_input_grad[0]
         g = torch.empty_like(a) if want_grad else None
         out = torch.empty(2, dtype=torch.float32, device=dev)
