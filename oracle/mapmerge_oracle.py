@@ -8,8 +8,8 @@
 * slerp: SLAM/utils.py:593-652 -- linear interpolation where |dot| of the normalised quaternions exceeds 0.9995 or is NaN
   (a zero quaternion), spherical otherwise; the interpolation uses the un-normalised inputs.
 
-Pinned to tests/golden/history_merge.npz, produced by the reference's unmodified `slerp` inside the expressions of
-`history_merge` (tests/golden/make_history_merge_golden.py)."""
+Pinned to tests/golden/history_merge.npz, produced by executing the reference's own `history_merge` method (compiled unchanged
+from its file) with its unmodified `slerp` (tests/golden/make_history_merge_golden.py)."""
 import numpy as np
 
 F32 = np.float32

@@ -250,7 +250,7 @@ def _close_fp32(a, b, ulps=2):
 @pytest.mark.parametrize("name", sorted(helpers.HISTORY_MERGE_SIZES))
 @pytest.mark.parametrize("max_weight", [0.5, 0.9])
 def test_history_merge_matches_reference_golden(cuda_device, name, max_weight):
-    """mapoptim.history_merge (one kernel, in place) against the golden outputs of the reference's own expressions with its
+    """mapoptim.history_merge (one kernel, in place) against the golden outputs of the reference's own history_merge method with its
     unmodified slerp (tests/golden/history_merge.npz) and against the numpy oracle. The lerps are the same fp32 operations in
     the same order; the rotation is bounded per row by the conditioning of slerp (helpers.slerp_tolerance)."""
     import os

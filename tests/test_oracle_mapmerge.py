@@ -1,5 +1,5 @@
 """CPU test of oracle/mapmerge_oracle.py: Mapping.history_merge restated in numpy against tests/golden/history_merge.npz,
-the outputs of the reference's own expressions with its unmodified slerp (tests/golden/make_history_merge_golden.py)."""
+the outputs of the reference's own history_merge method with its unmodified slerp (tests/golden/make_history_merge_golden.py)."""
 import os
 
 import numpy as np
