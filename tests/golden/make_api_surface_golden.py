@@ -13,14 +13,16 @@ import os
 
 REF = "/root/reference"
 RAST = "submodules/diff-gaussian-rasterizer-depth/diff_gaussian_rasterization_depth/__init__.py"
-FILES = {"rasterizer": RAST, "render": "SLAM/render.py", "icp": "SLAM/icp.py"}
+FILES = {"rasterizer": RAST, "render": "SLAM/render.py", "icp": "SLAM/icp.py", "utils": "SLAM/utils.py"}
 METHODS = {
     "rasterizer": {"GaussianRasterizer": ["__init__", "markVisible", "forward"]},
     "render": {"Renderer": ["__init__", "render"]},
     "icp": {"ICP": ["__init__", "icp"], "IcpTracker": ["__init__", "update_curr_status", "move_last_status", "update_last_status",
                                                        "predict_pose"]},
 }
-FUNCTIONS = {"rasterizer": ["rasterize_gaussians"], "icp": ["point2plane_loss"]}
+FUNCTIONS = {"rasterizer": ["rasterize_gaussians"], "icp": ["point2plane_loss"],
+             "utils": ["pixelmask2tilemask", "transmission2tilemask", "colorerror2tilemask", "bilateralFilter_torch"]}
+CUDA_UTILS_H = "submodules/cuda_utils/cuda_utils.h"   # C++ declaration behind `cuda_utils._C.accumulate_gaussian_error`
 
 
 def signature(fn):
@@ -67,6 +69,10 @@ def main():
             entry["tracker_args_read"] = sorted({n.attr for n in ast.walk(init) if isinstance(n, ast.Attribute)
                                                  and isinstance(n.value, ast.Name) and n.value.id == "args"})
         out[key] = entry
+    import re
+    decl = re.search(r"accumulate_gaussian_error\s*\((.*?)\)\s*;", open(os.path.join(REF, CUDA_UTILS_H)).read(), re.S).group(1)
+    out["cuda_utils"] = {"file": CUDA_UTILS_H, "functions": {"accumulate_gaussian_error": [
+        {"name": re.sub(r"[&*]", "", a.strip().split()[-1]), "default": None} for a in decl.split(",")]}}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "api_surface.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print("wrote", path)

@@ -168,3 +168,15 @@ def test_grad_buffer_and_visible_rows_context_managers_nest_and_restore():
     assert rz._GRAD_BUFFERS[0] is None                                                   # restored on an exception too
     prev = rz.set_grad_record_hook(print)
     assert prev is None and rz.set_grad_record_hook(None) is print
+
+
+def test_map_statistics_and_frame_helpers_keep_the_reference_signatures():
+    """SLAM/utils.py tile-mask builders and bilateralFilter_torch; the C++ declaration of cuda_utils' accumulate_gaussian_error
+    (positional in the reference's only call, mapper.py:546-559: same order, same names here)."""
+    from rtg_slam_b200 import frameprep, mapstats
+    want = SURFACE["utils"]["functions"]
+    for name in ("pixelmask2tilemask", "transmission2tilemask", "colorerror2tilemask"):
+        assert _params(getattr(mapstats, name)) == _expect(want[name]), name
+    assert _params(frameprep.bilateralFilter_torch) == _expect(want["bilateralFilter_torch"])
+    assert [n for n, _ in _params(mapstats.accumulate_gaussian_error)] == \
+        [a["name"] for a in SURFACE["cuda_utils"]["functions"]["accumulate_gaussian_error"]]
